@@ -1,0 +1,21 @@
+"""B200-native Levenberg-Marquardt bundle adjustment (drop-in for the reference's
+``lib/bundle_adjustment.py::BundleAdjuster``).
+
+Only the hot path lives here: ``csrc/`` (sm_100a CUDA kernels + the C-ABI of
+``include/ba_b200.h``), the ctypes binding, and the host-side mirror of the reference class.
+Importing the package does not load the CUDA library; constructing an engine does, and
+fails loudly if it is missing (there is no CPU fallback).
+"""
+from . import scenes  # noqa: F401
+
+
+def __getattr__(name):
+    if name in ("BundleAdjuster", "ObservationList"):
+        from . import bundle_adjuster
+
+        return getattr(bundle_adjuster, name)
+    if name == "Engine":
+        from . import engine
+
+        return engine.Engine
+    raise AttributeError(name)

@@ -1,0 +1,198 @@
+"""Generate ``tests/golden/*.npz`` by running the UNMODIFIED reference.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU box):
+
+    python oracle/gen_golden.py
+
+It imports ``/root/reference/lib/bundle_adjustment.py`` as-is (numpy + scipy only) and
+records, for each case, the BA inputs, the per-iteration cost trajectory from
+``get_log()``, the final ``(X, K, R, t)``, the printed iteration lines, and -- for the
+small cases -- the intermediates of the first linearisation and first damped solve.
+matplotlib is not installed here, so a no-op stub is injected for the script run (the
+reference's ``lib/visualization.py:1`` imports it); no reference source is copied.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import runpy
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+
+def _stub_matplotlib():
+    class _Anything:
+        def __getattr__(self, name):
+            return _Anything()
+
+        def __call__(self, *a, **k):
+            return _Anything()
+
+        def __iter__(self):
+            return iter(())
+
+    mpl = types.ModuleType("matplotlib")
+    plt = types.ModuleType("matplotlib.pyplot")
+    plt.__getattr__ = lambda name: _Anything()  # type: ignore[attr-defined]
+    plt.fignum_exists = lambda *_: False  # ends lib/visualization.py:175's loop at once
+    mpl.pyplot = plt
+    sys.modules.setdefault("matplotlib", mpl)
+    sys.modules.setdefault("matplotlib.pyplot", plt)
+
+
+def _run_reference(x, X0, K0, R0, t0, axis, vis=None, f0=1.0, scale=2.0, tol=1e-8, max_iter=100):
+    from lib.bundle_adjustment import BundleAdjuster  # the real reference class
+
+    ba = BundleAdjuster(x, X0, K0, R0, t0, f0=f0, visibility_index=vis, axis=axis)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        X, K, R, t = ba.optimize(scale, tol, max_iter=max_iter, is_debug=True)
+    log = ba.get_log()
+    return dict(
+        X=X, K=K, R=R, t=t,
+        E=np.array([d["reprojection_error"] for d in log]),
+        log_points=np.stack([d["points"] for d in log]),
+        log_basis=np.stack([d["basis"] for d in log]),
+        log_pos=np.stack([d["pos"] for d in log]),
+        stdout=np.array(buf.getvalue()),
+    )
+
+
+def _first_linearisation(x, X0, K0, R0, t0, axis, vis=None, f0=1.0, c=1e-4):
+    """Intermediates of one linearisation + one damped solve through the reference's own
+    private methods (``lib/bundle_adjustment.py:103-152``), in the normalised frame."""
+    from lib.bundle_adjustment import BundleAdjuster
+
+    ba = BundleAdjuster(x, X0, K0, R0, t0, f0=f0, visibility_index=vis, axis=axis)
+    K = ba._get_K(ba._f, ba._u)
+    P, p, q, r = ba._calc_pqr(ba._X, K, ba._R, ba._t)
+    E = ba._calc_reprojection_error(p, q, r)
+    dpdX, dqdX, drdX = ba._calc_X_diff_pqr(P)
+    dpc, dqc, drc = ba._calc_camera_params_diff_pqr(p, q, r)
+    d_P = ba._calc_d_P(p, q, r, dpdX, dqdX, drdX)
+    d_F = ba._calc_d_F(p, q, r, dpc, dqc, drc)
+    matE = ba._calc_matE(p, q, r, dpdX, dqdX, drdX)
+    matF = ba._calc_matF(p, q, r, dpdX, dqdX, drdX, dpc, dqc, drc)
+    matG = ba._calc_matG(p, q, r, dpc, dqc, drc)
+    matEc = matE.copy()
+    i3 = np.arange(3)
+    matEc[:, i3, i3] *= 1 + c
+    matGc = matG.copy()
+    ig = np.arange(matG.shape[0])
+    matGc[ig, ig] *= 1 + c
+    Einv = np.linalg.inv(matEc)
+    FtEinv = matF.transpose(0, 2, 1) @ Einv
+    A = matGc - (FtEinv @ matF).sum(axis=0)
+    dXE = d_P.reshape(-1, 3)[..., None]
+    b = (FtEinv @ dXE).squeeze().sum(axis=0) - d_F
+    dxi = np.linalg.solve(A, b)
+    dX = -(Einv @ (matF @ dxi[:, None] + dXE)).squeeze()
+    tX = ba._update_3d_points(dX)
+    tf, tu, tt, tR = ba._update_camera_params(dxi)
+    _, tp, tq, tr = ba._calc_pqr(tX, ba._get_K(tf, tu), tR, tt)
+    E_trial = ba._calc_reprojection_error(tp, tq, tr)
+    # per-observation Jacobians (a, b)/r^2 in the reference's dense layout
+    r2 = r[..., None] ** 2
+    Jx = np.stack(((r[..., None] * dpdX - p[..., None] * drdX) / r2,
+                   (r[..., None] * dqdX - q[..., None] * drdX) / r2), axis=2)  # (N,M,2,3)
+    Jc = np.stack(((r[..., None] * dpc - p[..., None] * drc) / r2,
+                   (r[..., None] * dqc - q[..., None] * drc) / r2), axis=2)  # (N,M,2,9)
+    return dict(
+        nX=ba._X, nR=ba._R, nt=ba._t, nf=np.array(ba._f), nu=np.array(ba._u),
+        p=p, q=q, r=r, E0=np.array(E), d_P=d_P, d_F=d_F, matE=matE, matF=matF, matG=matG,
+        A=A, b=b, dxi=dxi, dX=dX, E_trial=np.array(E_trial), Jx=Jx, Jc=Jc, c=np.array(c),
+        tX=tX, tf=tf, tu=tu, tt=tt, tR=tR,
+    )
+
+
+def case_c1():
+    """Config 1: ``euclidiean_reconstruction.py`` run unchanged (seed 123); the BA inputs
+    it builds (self-calibration output) are captured by wrapping the class constructor."""
+    _stub_matplotlib()
+    import lib.bundle_adjustment as refmod
+
+    captured = {}
+    orig_init = refmod.BundleAdjuster.__init__
+
+    def spy(self, x, init_X, init_K, init_R, init_t, *a, **k):
+        captured.update(x=np.array(x), X0=np.array(init_X), K0=np.array(init_K),
+                        R0=np.array(init_R), t0=np.array(init_t), axis=np.array(k.get("axis")))
+        orig_init(self, x, init_X, init_K, init_R, init_t, *a, **k)
+
+    refmod.BundleAdjuster.__init__ = spy
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            runpy.run_path(os.path.join(REF, "euclidiean_reconstruction.py"), run_name="__main__")
+    finally:
+        refmod.BundleAdjuster.__init__ = orig_init
+    x, X0, K0, R0, t0 = (captured[k] for k in ("x", "X0", "K0", "R0", "t0"))
+    out = _run_reference(x, X0, K0, R0, t0, "x-up_z-forward")
+    out.update(x=x, X0=X0, K0=K0, R0=R0, t0=t0, axis=np.array("x-up_z-forward"), f0=np.array(1.0))
+    np.savez_compressed(os.path.join(OUT, "c1_euclid.npz"), **out)
+    print("c1_euclid: iterations", len(out["E"]) - 1, "E_final", repr(float(out["E"][-1])))
+
+
+def case_small(name, n_cams, n_points, seed, visibility, axis, flip=False, max_iter=100,
+               intermediates=True):
+    import ba_b200
+
+    scenes = ba_b200.submodule("scenes")
+    sc = scenes.make_scene(n_cams, n_points, seed=seed, visibility=visibility, axis=axis)
+    X0, K0, R0, t0 = sc.X0, sc.K0, sc.R0, sc.t0
+    if flip:
+        # exercise the reference's negative-`s` gauge quirk (:228-234): order the first two
+        # cameras so that sign((t1-t0)_world[k]) differs from sign((R0^T (t1-t0))[k])
+        k = 0 if axis == "x-right_z-forward" else 1
+        found = False
+        for a in range(n_cams):
+            for b in range(n_cams):
+                if a == b:
+                    continue
+                dt = t0[b] - t0[a]
+                if np.sign(dt[k]) * (R0[a].T @ dt)[k] < 0:
+                    found = True
+                    break
+            if found:
+                break
+        assert found, "no camera pair with the sign quirk; pick another seed"
+        order = [a, b] + [i for i in range(n_cams) if i not in (a, b)]
+        x, vis = sc.dense_x()
+        x, vis = x[:, order], vis[:, order]
+        K0, R0, t0 = K0[order], R0[order], t0[order]
+    else:
+        x, vis = sc.dense_x()
+    vis_arg = None if visibility >= 1.0 else vis
+    out = _run_reference(x, X0, K0, R0, t0, axis, vis=vis_arg, max_iter=max_iter)
+    if intermediates:
+        out.update({"lin_" + k: v for k, v in
+                    _first_linearisation(x, X0, K0, R0, t0, axis, vis=vis_arg).items()})
+    out.update(x=x, vis=vis, X0=X0, K0=K0, R0=R0, t0=t0, axis=np.array(axis), f0=np.array(1.0))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"{name}: iterations", len(out["E"]) - 1, "E_final", repr(float(out["E"][-1])))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    case_c1()
+    case_small("small_dense_xup", 6, 40, seed=11, visibility=1.0, axis="x-up_z-forward")
+    case_small("small_dense_xright", 5, 32, seed=12, visibility=1.0, axis="x-right_z-forward")
+    case_small("small_sparse_xup", 8, 60, seed=13, visibility=0.6, axis="x-up_z-forward")
+    case_small("small_sparse_xright", 7, 50, seed=14, visibility=0.5, axis="x-right_z-forward")
+    case_small("small_flip_xup", 6, 36, seed=15, visibility=1.0, axis="x-up_z-forward", flip=True)
+    case_small("mid_dense_xup", 20, 400, seed=16, visibility=1.0, axis="x-up_z-forward",
+               intermediates=False)
+    case_small("mid_sparse_xup", 24, 500, seed=17, visibility=0.3, axis="x-up_z-forward",
+               intermediates=False)
+
+
+if __name__ == "__main__":
+    main()
