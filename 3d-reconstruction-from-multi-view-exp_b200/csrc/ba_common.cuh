@@ -1,0 +1,210 @@
+// Shared definitions of the bundle-adjustment engine: engine object, error handling,
+// launch bookkeeping and small device helpers.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "ba_b200.h"
+
+namespace ba {
+
+// ------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define BA_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _err = (expr);                                                             \
+    if (_err != cudaSuccess) {                                                             \
+      ::ba::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_err), __FILE__,  \
+                      __LINE__);                                                           \
+      return BA_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define BA_TRY(expr)                 \
+  do {                               \
+    int _st = (expr);                \
+    if (_st != BA_OK) return _st;    \
+  } while (0)
+
+// ------------------------------------------------------------------------------------
+// constants of the data layout
+// ------------------------------------------------------------------------------------
+constexpr int kCamTab = 16;   // doubles per camera in the derived table (128 B rows)
+constexpr int kJP = 8;        // doubles per observation, point-side row: e(2), de/dX (2x3)
+constexpr int kJC = 20;       // doubles per observation, camera-side row: e(2), de/dcam (2x9)
+constexpr int kUPart = 54;    // 45 unique entries of U_i + 9 of dF_i
+constexpr int kCholNB = 64;   // panel width of the blocked Cholesky
+constexpr int kMaxRecords = 4096;
+
+// Pinned camera parameters (gauge): camera 0 keeps f,u0,v0 only; camera 1 loses one
+// translation component (reference lib/bundle_adjustment.py:62-72).  Bit a set = parameter a
+// of that camera is removed from the unknowns.
+__host__ __device__ inline uint32_t gauge_mask(int cam, int axis) {
+  return cam == 0 ? 0x1F8u : (cam == 1 ? (1u << (3 + axis)) : 0u);
+}
+
+struct CamState {
+  double* f = nullptr;  // [M]
+  double* u = nullptr;  // [M][2]
+  double* R = nullptr;  // [M][3][3] row-major, camera-to-world
+  double* t = nullptr;  // [M][3]
+};
+
+enum ProfGroup { PG_K1 = 0, PG_K2, PG_K3, PG_K4, PG_COST, PG_OTHER, PG_COUNT };
+
+struct ProfSlot {
+  double ms = 0.0;
+  int64_t launches = 0;
+};
+
+}  // namespace ba
+
+// The opaque engine of the C ABI.
+struct ba_engine {
+  ba_problem prob{};
+  int64_t N = 0, nobs = 0;
+  int M = 0, dense = 0, axis = 0, device = 0;
+  double f0 = 1.0;
+  int num_sms = 148;
+
+  // reduced system layout: n_full = 9M unknown slots (gauge entries pinned, not deleted),
+  // row rhs_row = 9M carries the right-hand side, n_pad = padded order = leading dimension
+  int n_full = 0, rhs_row = 0, n_pad = 0;
+  int syrk_tile = 128, syrk_splits = 1;
+  int64_t k_pad = 0;  // padded 3N (rows of Yt)
+
+  // observations (CSR by point) and camera-major index
+  int64_t* obs_ptr = nullptr;
+  int32_t* obs_cam = nullptr;  // null when dense
+  int32_t* obs_pt = nullptr;   // null when dense
+  double* obs_xy = nullptr;
+  int64_t* cam_ptr = nullptr;  // [M+1] (sparse)
+  int32_t* cm_perm = nullptr;  // [nobs] observation ids sorted by camera (sparse)
+  int64_t max_pt_obs = 0;
+  bool have_obs = false, have_state = false;
+
+  // state: [0] current, [1] trial
+  double* X[2] = {nullptr, nullptr};
+  ba::CamState cam[2];
+  double* camtab[2] = {nullptr, nullptr};
+
+  // linearisation
+  double *JP = nullptr, *JC = nullptr, *V = nullptr, *GPT = nullptr;
+  double *Upart = nullptr;  // [M][cam_chunks][54]
+  double *Uloc = nullptr;   // [M*81 | M*9] this engine's U_i and dF_i (before any all-reduce)
+  int cam_chunks = 1;
+
+  // per solve
+  double *LINV = nullptr, *Z = nullptr;
+  double* Yt = nullptr;   // dense: [k_pad][n_pad]
+  double* Ysp = nullptr;  // sparse: [nobs][27]
+  double* red = nullptr;  // [n_pad*n_pad | M*81 | M*9]
+  int64_t red_len = 0;
+  double* Spart = nullptr;  // split-K partial tiles
+  double* Lt = nullptr;     // Cholesky panel, k-major copy [kCholNB][n_pad]
+  double* dxi = nullptr;    // [M][9]
+  double* cost_part = nullptr;
+  int cost_blocks = 0;
+  double* cost_buf = nullptr;  // [2]
+
+  ba_lm_state* ctl = nullptr;       // device
+  ba_iter_record* rec = nullptr;    // device [kMaxRecords]
+  ba_lm_state* ctl_host = nullptr;  // pinned
+
+  // profiling
+  bool profiling = false;
+  ba::ProfSlot prof[ba::PG_COUNT];
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  double* P() const { return red; }
+  double* U() const { return red + (int64_t)n_pad * n_pad; }
+  double* GCAM() const { return red + (int64_t)n_pad * n_pad + (int64_t)M * 81; }
+};
+
+namespace ba {
+
+extern int64_t g_launch_count;
+
+// Brackets a group of launches with CUDA events when profiling is on.
+struct ProfScope {
+  ba_engine* e;
+  int group;
+  cudaStream_t s;
+  int64_t launches_before;
+  ProfScope(ba_engine* e_, int group_, cudaStream_t s_) : e(e_), group(group_), s(s_) {
+    launches_before = g_launch_count;
+    if (e->profiling) cudaEventRecord(e->ev0, s);
+  }
+  ~ProfScope() {
+    e->prof[group].launches += g_launch_count - launches_before;
+    if (e->profiling) {
+      cudaEventRecord(e->ev1, s);
+      cudaEventSynchronize(e->ev1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+      e->prof[group].ms += ms;
+    }
+  }
+};
+
+#define BA_LAUNCH_CHECK()                                                       \
+  do {                                                                          \
+    ::ba::g_launch_count++;                                                     \
+    cudaError_t _err = cudaGetLastError();                                      \
+    if (_err != cudaSuccess) {                                                  \
+      ::ba::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_err), \
+                      __FILE__, __LINE__);                                      \
+      return BA_ERR_CUDA;                                                       \
+    }                                                                           \
+  } while (0)
+
+// ------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// Deterministic block sum (fixed tree): every thread gets the result.  `scratch` >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  double r = 0.0;
+  for (int w = 0; w < nw; ++w) r += scratch[w];
+  return r;
+}
+#endif
+
+// kernel launchers implemented in the .cu files (each returns a ba_status)
+int launch_cam_prep(ba_engine* e, int which, cudaStream_t s);
+int launch_cost(ba_engine* e, int which, int slot, cudaStream_t s);
+int launch_k1(ba_engine* e, cudaStream_t s, bool conditional);
+int launch_k2a(ba_engine* e, cudaStream_t s, bool conditional);
+int launch_camera_blocks(ba_engine* e, cudaStream_t s, bool conditional);
+int launch_k2b(ba_engine* e, bool conditional, double c_host, cudaStream_t s);
+int launch_k3(ba_engine* e, bool conditional, cudaStream_t s);
+int syrk_choose_splits(int n_pad, int tile, int64_t k_pad, int num_sms);
+int launch_assemble(ba_engine* e, bool conditional, double c_host, cudaStream_t s);
+int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s);
+int launch_update_trial(ba_engine* e, bool conditional, cudaStream_t s);
+int launch_decide(ba_engine* e, cudaStream_t s);
+int launch_lm_begin(ba_engine* e, double scale, double tol, int max_iter, int max_retries,
+                    cudaStream_t s);
+int build_camera_major_index(ba_engine* e, cudaStream_t s);
+int fp64_peak(int device, int use_dmma, double* tflops);
+
+}  // namespace ba

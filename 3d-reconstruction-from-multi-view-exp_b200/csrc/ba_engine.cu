@@ -1,0 +1,592 @@
+// Engine object and the C ABI of include/ba_b200.h: memory layout in HBM, observation
+// ingestion (camera-major index built on the device), phase sequencing of the LM loop.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <cstdarg>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "ba_common.cuh"
+
+namespace ba {
+
+int64_t g_launch_count = 0;
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int launch_lm_adopt(ba_engine* e, cudaStream_t s);
+
+template <typename T>
+static int dev_alloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  return BA_OK;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+static int copy_in(void* dst, const void* src, size_t bytes, int mem, cudaStream_t s) {
+  if (bytes == 0) return BA_OK;
+  BA_CUDA(cudaMemcpyAsync(dst, src, bytes,
+                          mem == BA_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  return BA_OK;
+}
+static int copy_out(void* dst, const void* src, size_t bytes, int mem, cudaStream_t s) {
+  if (bytes == 0) return BA_OK;
+  BA_CUDA(cudaMemcpyAsync(dst, src, bytes,
+                          mem == BA_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  return BA_OK;
+}
+
+// ---- observation index kernels ---------------------------------------------------------------
+__global__ void fill_obs_pt_kernel(int64_t N, const int64_t* __restrict__ obs_ptr,
+                                   int32_t* __restrict__ obs_pt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = warp; j < N; j += nwarps)
+    for (int64_t o = obs_ptr[j] + lane; o < obs_ptr[j + 1]; o += 32) obs_pt[o] = (int32_t)j;
+}
+
+__global__ void iota_kernel(int64_t n, int32_t* __restrict__ v) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) v[k] = (int32_t)k;
+}
+
+// cam_ptr[i] = first position in the camera-sorted key array with key >= i
+__global__ void cam_ptr_kernel(int M, int64_t n, const int32_t* __restrict__ keys,
+                               int64_t* __restrict__ cam_ptr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > M) return;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < i) lo = mid + 1; else hi = mid;
+  }
+  cam_ptr[i] = lo;
+}
+
+// Stable (hence deterministic) radix sort of observation ids by camera: cm_perm, cam_ptr.
+int build_camera_major_index(ba_engine* e, cudaStream_t s) {
+  const int64_t n = e->nobs;
+  if (n >= (int64_t)1 << 31) {
+    set_error("more than 2^31 observations per engine are not supported");
+    return BA_ERR_INVALID;
+  }
+  int32_t *keys_out = nullptr, *vals_in = nullptr;
+  BA_TRY(dev_alloc(&keys_out, (size_t)n));
+  BA_TRY(dev_alloc(&vals_in, (size_t)n));
+  iota_kernel<<<e->num_sms * 4, 256, 0, s>>>(n, vals_in);
+  BA_LAUNCH_CHECK();
+  int bits = 1;
+  while ((1 << bits) < e->M) ++bits;
+  size_t tmp_bytes = 0;
+  BA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, e->obs_cam, keys_out, vals_in,
+                                          e->cm_perm, (int)n, 0, bits, s));
+  void* tmp = nullptr;
+  BA_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+  BA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, e->obs_cam, keys_out, vals_in, e->cm_perm,
+                                          (int)n, 0, bits, s));
+  cam_ptr_kernel<<<(e->M + 1 + 127) / 128, 128, 0, s>>>(e->M, n, keys_out, e->cam_ptr);
+  BA_LAUNCH_CHECK();
+  BA_CUDA(cudaStreamSynchronize(s));
+  cudaFree(tmp);
+  cudaFree(keys_out);
+  cudaFree(vals_in);
+  return BA_OK;
+}
+
+static void free_engine(ba_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  void* ptrs[] = {e->obs_ptr, e->obs_cam, e->obs_pt, e->obs_xy, e->cam_ptr, e->cm_perm, e->X[0],
+                  e->X[1], e->cam[0].f, e->cam[1].f, e->camtab[0], e->camtab[1], e->JP, e->JC, e->V,
+                  e->GPT, e->Upart, e->Uloc, e->LINV, e->Z, e->Yt, e->Ysp, e->red, e->Spart, e->Lt,
+                  e->dxi, e->cost_part, e->cost_buf, e->ctl, e->rec};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (e->ctl_host) cudaFreeHost(e->ctl_host);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  delete e;
+}
+
+static int alloc_cam(CamState* c, int M) {
+  double* base = nullptr;
+  BA_TRY(dev_alloc(&base, (size_t)15 * M));
+  c->f = base;
+  c->u = base + M;
+  c->R = base + 3 * (size_t)M;
+  c->t = base + 12 * (size_t)M;
+  return BA_OK;
+}
+
+static int create_engine(const ba_problem* p, ba_engine** out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: this engine has no CPU path");
+    return BA_ERR_NO_DEVICE;
+  }
+  if (!p || !out) { set_error("null argument"); return BA_ERR_INVALID; }
+  if (p->axis != BA_AXIS_X_RIGHT && p->axis != BA_AXIS_X_UP) {
+    set_error("unknown gauge axis %d", p->axis);
+    return BA_ERR_INVALID;
+  }
+  if (p->n_cams < 2 || p->n_points < 1 || p->n_obs < 1 || !(p->f0 != 0.0)) {
+    set_error("need >= 2 cameras, >= 1 point, >= 1 observation and f0 != 0");
+    return BA_ERR_INVALID;
+  }
+  if (p->dense && p->n_obs != p->n_points * (int64_t)p->n_cams) {
+    set_error("dense problem needs n_obs == n_points * n_cams");
+    return BA_ERR_INVALID;
+  }
+  if (p->device < 0 || p->device >= ndev) {
+    set_error("device %d out of range (%d devices)", p->device, ndev);
+    return BA_ERR_INVALID;
+  }
+  BA_CUDA(cudaSetDevice(p->device));
+  ba_engine* e = new (std::nothrow) ba_engine();
+  if (!e) { set_error("out of host memory"); return BA_ERR_CUDA; }
+  e->prob = *p;
+  e->N = p->n_points; e->nobs = p->n_obs; e->M = p->n_cams; e->dense = p->dense ? 1 : 0;
+  e->axis = p->axis; e->device = p->device; e->f0 = p->f0;
+  cudaDeviceProp prop;
+  BA_CUDA(cudaGetDeviceProperties(&prop, p->device));
+  e->num_sms = prop.multiProcessorCount;
+
+  e->n_full = 9 * e->M;
+  e->rhs_row = e->n_full;
+  const int n_aug = e->n_full + 1;
+  e->syrk_tile = n_aug <= 1024 ? 64 : 128;
+  e->n_pad = round_up(n_aug, e->syrk_tile);
+  e->k_pad = round_up64(3 * e->N, 16);
+  e->syrk_splits = syrk_choose_splits(e->n_pad, e->syrk_tile, e->k_pad, e->num_sms);
+  e->cam_chunks = (4 * e->num_sms + e->M - 1) / e->M;
+  if (e->cam_chunks < 1) e->cam_chunks = 1;
+  {
+    const int64_t per_cam = e->nobs / e->M + 1;
+    const int64_t maxc = per_cam / 256 > 0 ? per_cam / 256 : 1;
+    if (e->cam_chunks > maxc) e->cam_chunks = (int)maxc;
+  }
+  {
+    const int64_t b = (e->nobs + 255) / 256;
+    const int64_t cap = (int64_t)e->num_sms * 4;
+    e->cost_blocks = (int)(b < cap ? b : cap);
+  }
+
+  int st = BA_OK;
+#define A(expr) if (st == BA_OK) st = (expr)
+  A(dev_alloc(&e->obs_ptr, (size_t)e->N + 1));
+  A(dev_alloc(&e->obs_xy, (size_t)e->nobs * 2));
+  if (!e->dense) {
+    A(dev_alloc(&e->obs_cam, (size_t)e->nobs));
+    A(dev_alloc(&e->obs_pt, (size_t)e->nobs));
+    A(dev_alloc(&e->cm_perm, (size_t)e->nobs));
+    A(dev_alloc(&e->cam_ptr, (size_t)e->M + 1));
+  }
+  for (int w = 0; w < 2; ++w) {
+    A(dev_alloc(&e->X[w], (size_t)3 * e->N));
+    A(alloc_cam(&e->cam[w], e->M));
+    A(dev_alloc(&e->camtab[w], (size_t)e->M * kCamTab));
+  }
+  A(dev_alloc(&e->JP, (size_t)e->nobs * kJP));
+  A(dev_alloc(&e->JC, (size_t)e->nobs * kJC));
+  A(dev_alloc(&e->V, (size_t)6 * e->N));
+  A(dev_alloc(&e->GPT, (size_t)3 * e->N));
+  A(dev_alloc(&e->Upart, (size_t)e->M * e->cam_chunks * kUPart));
+  A(dev_alloc(&e->Uloc, (size_t)e->M * 90));
+  A(dev_alloc(&e->LINV, (size_t)6 * e->N));
+  A(dev_alloc(&e->Z, (size_t)3 * e->N));
+  e->red_len = (int64_t)e->n_pad * e->n_pad + (int64_t)e->M * 90;
+  A(dev_alloc(&e->red, (size_t)e->red_len));
+  if (e->dense) {
+    A(dev_alloc(&e->Yt, (size_t)e->k_pad * e->n_pad));
+    const int nt1 = e->n_pad / e->syrk_tile;
+    A(dev_alloc(&e->Spart, (size_t)e->syrk_splits * (nt1 * (nt1 + 1) / 2) * e->syrk_tile * e->syrk_tile));
+  } else {
+    A(dev_alloc(&e->Ysp, (size_t)e->nobs * 27));
+  }
+  A(dev_alloc(&e->Lt, (size_t)kCholNB * e->n_pad));
+  A(dev_alloc(&e->dxi, (size_t)e->n_full));
+  A(dev_alloc(&e->cost_part, (size_t)e->num_sms * 16 + 1024));
+  A(dev_alloc(&e->cost_buf, (size_t)2));
+  A(dev_alloc(&e->ctl, (size_t)1));
+  A(dev_alloc(&e->rec, (size_t)kMaxRecords));
+#undef A
+  if (st == BA_OK && cudaMallocHost(reinterpret_cast<void**>(&e->ctl_host), sizeof(ba_lm_state)) != cudaSuccess) {
+    set_error("cudaMallocHost failed");
+    st = BA_ERR_CUDA;
+  }
+  if (st == BA_OK) {
+    cudaEventCreate(&e->ev0);
+    cudaEventCreate(&e->ev1);
+    cudaMemset(e->red, 0, (size_t)e->red_len * sizeof(double));
+    if (e->Yt) cudaMemset(e->Yt, 0, (size_t)e->k_pad * e->n_pad * sizeof(double));
+    cudaMemset(e->ctl, 0, sizeof(ba_lm_state));
+    cudaMemset(e->cost_buf, 0, 2 * sizeof(double));
+    cudaMemset(e->dxi, 0, (size_t)e->n_full * sizeof(double));
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      set_error("device initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      st = BA_ERR_CUDA;
+    }
+  }
+  if (st != BA_OK) {
+    free_engine(e);
+    return st;
+  }
+  *out = e;
+  return BA_OK;
+}
+
+static int check_ready(ba_engine* e) {
+  if (!e) { set_error("null engine"); return BA_ERR_INVALID; }
+  if (!e->have_obs || !e->have_state) {
+    set_error("observations and state must be set first");
+    return BA_ERR_STATE;
+  }
+  if (cudaSetDevice(e->device) != cudaSuccess) { set_error("cudaSetDevice failed"); return BA_ERR_CUDA; }
+  return BA_OK;
+}
+
+static int phase_reduce(ba_engine* e, bool conditional, double c_host, cudaStream_t s) {
+  if (conditional) {
+    BA_TRY(launch_lm_adopt(e, s));
+    { ProfScope ps(e, PG_K1, s); BA_TRY(launch_k1(e, s, true)); }
+    { ProfScope ps(e, PG_K2, s); BA_TRY(launch_k2a(e, s, true)); BA_TRY(launch_camera_blocks(e, s, true)); }
+  }
+  { ProfScope ps(e, PG_K2, s); BA_TRY(launch_k2b(e, conditional, c_host, s)); }
+  { ProfScope ps(e, PG_K3, s); BA_TRY(launch_k3(e, conditional, s)); }
+  return BA_OK;
+}
+
+static int phase_solve(ba_engine* e, bool conditional, double c_host, cudaStream_t s) {
+  ProfScope ps(e, PG_K4, s);
+  BA_TRY(launch_assemble(e, conditional, c_host, s));
+  BA_TRY(launch_cholesky_solve(e, conditional, s));
+  BA_TRY(launch_update_trial(e, conditional, s));
+  return BA_OK;
+}
+
+static int read_ctl(ba_engine* e, ba_lm_state* out, cudaStream_t s) {
+  BA_CUDA(cudaMemcpyAsync(e->ctl_host, e->ctl, sizeof(ba_lm_state), cudaMemcpyDeviceToHost, s));
+  BA_CUDA(cudaStreamSynchronize(s));
+  if (out) *out = *e->ctl_host;
+  return BA_OK;
+}
+
+static int status_from_ctl(const ba_lm_state& st) {
+  if (st.status == BA_ERR_SINGULAR) {
+    set_error("Singular matrix");  // numpy.linalg.LinAlgError text of the reference (:128)
+    return BA_ERR_SINGULAR;
+  }
+  if (st.status == BA_ERR_STALL) {
+    set_error("inner LM loop exceeded %d retries without decreasing the cost", st.max_retries);
+    return BA_ERR_STALL;
+  }
+  return BA_OK;
+}
+
+}  // namespace ba
+
+using namespace ba;
+
+extern "C" {
+
+int ba_version(void) { return BA_B200_VERSION; }
+const char* ba_last_error(void) { return g_err; }
+
+int ba_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int ba_create(const ba_problem* problem, ba_engine** out) { return create_engine(problem, out); }
+
+int ba_destroy(ba_engine* e) {
+  free_engine(e);
+  return BA_OK;
+}
+
+int ba_set_observations(ba_engine* e, const int64_t* obs_ptr, const int32_t* obs_cam,
+                        const double* obs_xy, int mem, void* stream) {
+  if (!e || !obs_xy || (!e->dense && (!obs_ptr || !obs_cam))) {
+    set_error("null argument");
+    return BA_ERR_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  BA_CUDA(cudaSetDevice(e->device));
+  if (mem == BA_MEM_HOST && obs_ptr) {
+    if (obs_ptr[0] != 0 || obs_ptr[e->N] != e->nobs) {
+      set_error("obs_ptr must start at 0 and end at n_obs");
+      return BA_ERR_INVALID;
+    }
+    for (int64_t j = 0; j < e->N; ++j)
+      if (obs_ptr[j + 1] < obs_ptr[j]) { set_error("obs_ptr not monotone"); return BA_ERR_INVALID; }
+    if (!e->dense)
+      for (int64_t o = 0; o < e->nobs; ++o)
+        if (obs_cam[o] < 0 || obs_cam[o] >= e->M) { set_error("camera index out of range"); return BA_ERR_INVALID; }
+  }
+  if (obs_ptr) {
+    BA_TRY(copy_in(e->obs_ptr, obs_ptr, ((size_t)e->N + 1) * sizeof(int64_t), mem, s));
+  } else {
+    std::vector<int64_t> p((size_t)e->N + 1);
+    for (int64_t j = 0; j <= e->N; ++j) p[(size_t)j] = j * e->M;
+    BA_CUDA(cudaMemcpyAsync(e->obs_ptr, p.data(), p.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    BA_CUDA(cudaStreamSynchronize(s));
+  }
+  BA_TRY(copy_in(e->obs_xy, obs_xy, (size_t)e->nobs * 2 * sizeof(double), mem, s));
+  if (!e->dense) {
+    BA_TRY(copy_in(e->obs_cam, obs_cam, (size_t)e->nobs * sizeof(int32_t), mem, s));
+    fill_obs_pt_kernel<<<e->num_sms * 8, 256, 0, s>>>(e->N, e->obs_ptr, e->obs_pt);
+    BA_LAUNCH_CHECK();
+    BA_TRY(build_camera_major_index(e, s));
+  }
+  BA_CUDA(cudaStreamSynchronize(s));
+  e->have_obs = true;
+  return BA_OK;
+}
+
+int ba_set_state(ba_engine* e, const double* X, const double* R, const double* t, const double* f,
+                 const double* u, int mem, void* stream) {
+  if (!e) { set_error("null engine"); return BA_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  BA_CUDA(cudaSetDevice(e->device));
+  const size_t d = sizeof(double);
+  if (X) BA_TRY(copy_in(e->X[0], X, (size_t)3 * e->N * d, mem, s));
+  if (R) BA_TRY(copy_in(e->cam[0].R, R, (size_t)9 * e->M * d, mem, s));
+  if (t) BA_TRY(copy_in(e->cam[0].t, t, (size_t)3 * e->M * d, mem, s));
+  if (f) BA_TRY(copy_in(e->cam[0].f, f, (size_t)e->M * d, mem, s));
+  if (u) BA_TRY(copy_in(e->cam[0].u, u, (size_t)2 * e->M * d, mem, s));
+  if (mem == BA_MEM_HOST) BA_CUDA(cudaStreamSynchronize(s));
+  e->have_state = true;
+  return BA_OK;
+}
+
+int ba_get_state(ba_engine* e, int which, double* X, double* R, double* t, double* f, double* u,
+                 int mem, void* stream) {
+  if (!e || (which != 0 && which != 1)) { set_error("bad argument"); return BA_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  BA_CUDA(cudaSetDevice(e->device));
+  const size_t d = sizeof(double);
+  if (X) BA_TRY(copy_out(X, e->X[which], (size_t)3 * e->N * d, mem, s));
+  if (R) BA_TRY(copy_out(R, e->cam[which].R, (size_t)9 * e->M * d, mem, s));
+  if (t) BA_TRY(copy_out(t, e->cam[which].t, (size_t)3 * e->M * d, mem, s));
+  if (f) BA_TRY(copy_out(f, e->cam[which].f, (size_t)e->M * d, mem, s));
+  if (u) BA_TRY(copy_out(u, e->cam[which].u, (size_t)2 * e->M * d, mem, s));
+  if (mem == BA_MEM_HOST) BA_CUDA(cudaStreamSynchronize(s));
+  return BA_OK;
+}
+
+int ba_cost(ba_engine* e, int which, void* stream) {
+  BA_TRY(check_ready(e));
+  if (which != 0 && which != 1) { set_error("bad state selector"); return BA_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfScope ps(e, PG_COST, s);
+  BA_TRY(launch_cam_prep(e, which, s));
+  return launch_cost(e, which, which, s);
+}
+
+int ba_linearize(ba_engine* e, void* stream) {
+  BA_TRY(check_ready(e));
+  cudaStream_t s = (cudaStream_t)stream;
+  { ProfScope ps(e, PG_K1, s); BA_TRY(launch_k1(e, s, false)); }
+  { ProfScope ps(e, PG_K2, s); BA_TRY(launch_k2a(e, s, false)); BA_TRY(launch_camera_blocks(e, s, false)); }
+  return BA_OK;
+}
+
+int ba_build_reduced(ba_engine* e, double c, void* stream) {
+  BA_TRY(check_ready(e));
+  return phase_reduce(e, false, c, (cudaStream_t)stream);
+}
+
+int ba_solve_trial(ba_engine* e, double c, void* stream) {
+  BA_TRY(check_ready(e));
+  return phase_solve(e, false, c, (cudaStream_t)stream);
+}
+
+int ba_lm_begin(ba_engine* e, double scale_factor, double delta_tol, int max_iter, int max_retries,
+                void* stream) {
+  BA_TRY(check_ready(e));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (max_retries <= 0) max_retries = 200;
+  BA_TRY(launch_lm_begin(e, scale_factor, delta_tol, max_iter, max_retries, s));
+  ProfScope ps(e, PG_COST, s);
+  BA_TRY(launch_cam_prep(e, 0, s));
+  return launch_cost(e, 0, 0, s);
+}
+
+int ba_lm_phase_reduce(ba_engine* e, void* stream) {
+  BA_TRY(check_ready(e));
+  return phase_reduce(e, true, 0.0, (cudaStream_t)stream);
+}
+
+int ba_lm_phase_solve(ba_engine* e, void* stream) {
+  BA_TRY(check_ready(e));
+  return phase_solve(e, true, 0.0, (cudaStream_t)stream);
+}
+
+int ba_lm_phase_decide(ba_engine* e, void* stream) {
+  BA_TRY(check_ready(e));
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfScope ps(e, PG_OTHER, s);
+  return launch_decide(e, s);
+}
+
+int ba_lm_state_get(ba_engine* e, ba_lm_state* out, void* stream) {
+  if (!e || !out) { set_error("null argument"); return BA_ERR_INVALID; }
+  BA_CUDA(cudaSetDevice(e->device));
+  return read_ctl(e, out, (cudaStream_t)stream);
+}
+
+int ba_lm_iterate(ba_engine* e, ba_lm_state* out, void* stream) {
+  BA_TRY(check_ready(e));
+  cudaStream_t s = (cudaStream_t)stream;
+  ba_lm_state st;
+  BA_TRY(read_ctl(e, &st, s));
+  const int count0 = st.count;
+  while (!st.done && st.count == count0) {
+    BA_TRY(phase_reduce(e, true, 0.0, s));
+    BA_TRY(phase_solve(e, true, 0.0, s));
+    { ProfScope ps(e, PG_OTHER, s); BA_TRY(launch_decide(e, s)); }
+    BA_TRY(read_ctl(e, &st, s));
+  }
+  if (out) *out = st;
+  return status_from_ctl(st);
+}
+
+int ba_lm_records(ba_engine* e, ba_iter_record* records, int max_records, int* n_records,
+                  void* stream) {
+  if (!e || !n_records) { set_error("null argument"); return BA_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  ba_lm_state st;
+  BA_TRY(read_ctl(e, &st, s));
+  int n = st.count < kMaxRecords ? st.count : kMaxRecords;
+  if (n > max_records) n = max_records;
+  if (n > 0 && records) {
+    BA_CUDA(cudaMemcpyAsync(records, e->rec, (size_t)n * sizeof(ba_iter_record), cudaMemcpyDeviceToHost, s));
+    BA_CUDA(cudaStreamSynchronize(s));
+  }
+  *n_records = n;
+  return BA_OK;
+}
+
+int ba_lm_run(ba_engine* e, double scale_factor, double delta_tol, int max_iter, int max_retries,
+              ba_iter_record* records, int max_records, int* n_records, ba_lm_state* final_state,
+              void* stream) {
+  BA_TRY(ba_lm_begin(e, scale_factor, delta_tol, max_iter, max_retries, stream));
+  cudaStream_t s = (cudaStream_t)stream;
+  ba_lm_state st;
+  std::memset(&st, 0, sizeof(st));
+  while (!st.done) {
+    BA_TRY(phase_reduce(e, true, 0.0, s));
+    BA_TRY(phase_solve(e, true, 0.0, s));
+    { ProfScope ps(e, PG_OTHER, s); BA_TRY(launch_decide(e, s)); }
+    BA_TRY(read_ctl(e, &st, s));
+  }
+  if (final_state) *final_state = st;
+  if (n_records) BA_TRY(ba_lm_records(e, records, max_records, n_records, stream));
+  return status_from_ctl(st);
+}
+
+int ba_reduce_buffer(ba_engine* e, void** device_ptr, int64_t* n_doubles) {
+  if (!e || !device_ptr || !n_doubles) { set_error("null argument"); return BA_ERR_INVALID; }
+  *device_ptr = e->red;
+  *n_doubles = e->red_len;
+  return BA_OK;
+}
+
+int ba_cost_buffer(ba_engine* e, void** device_ptr, int64_t* n_doubles) {
+  if (!e || !device_ptr || !n_doubles) { set_error("null argument"); return BA_ERR_INVALID; }
+  *device_ptr = e->cost_buf;
+  *n_doubles = 2;
+  return BA_OK;
+}
+
+static int buffer_info(ba_engine* e, int id, const double** p, int64_t* n) {
+  switch (id) {
+    case BA_BUF_JP: *p = e->JP; *n = e->nobs * kJP; break;
+    case BA_BUF_JC: *p = e->JC; *n = e->nobs * kJC; break;
+    case BA_BUF_V: *p = e->V; *n = 6 * e->N; break;
+    case BA_BUF_GPT: *p = e->GPT; *n = 3 * e->N; break;
+    case BA_BUF_U: *p = e->Uloc; *n = (int64_t)81 * e->M; break;
+    case BA_BUF_GCAM: *p = e->Uloc + (size_t)81 * e->M; *n = (int64_t)9 * e->M; break;
+    case BA_BUF_S: *p = e->red; *n = (int64_t)e->n_pad * e->n_pad; break;
+    case BA_BUF_DXI: *p = e->dxi; *n = e->n_full; break;
+    case BA_BUF_LINV: *p = e->LINV; *n = 6 * e->N; break;
+    case BA_BUF_Z: *p = e->Z; *n = 3 * e->N; break;
+    case BA_BUF_REDUCE: *p = e->red; *n = e->red_len; break;
+    case BA_BUF_COST: *p = e->cost_buf; *n = 2; break;
+    default: set_error("unknown buffer id %d", id); return BA_ERR_INVALID;
+  }
+  return BA_OK;
+}
+
+int ba_buffer_size(ba_engine* e, int id, int64_t* n_doubles) {
+  if (!e || !n_doubles) { set_error("null argument"); return BA_ERR_INVALID; }
+  const double* p;
+  return buffer_info(e, id, &p, n_doubles);
+}
+
+int ba_buffer_read(ba_engine* e, int id, double* host_out, int64_t n_doubles, void* stream) {
+  if (!e || !host_out) { set_error("null argument"); return BA_ERR_INVALID; }
+  const double* p;
+  int64_t n;
+  BA_TRY(buffer_info(e, id, &p, &n));
+  if (n_doubles != n) { set_error("buffer %d holds %lld doubles, caller asked for %lld", id, (long long)n, (long long)n_doubles); return BA_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  BA_CUDA(cudaSetDevice(e->device));
+  BA_CUDA(cudaMemcpyAsync(host_out, p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  BA_CUDA(cudaStreamSynchronize(s));
+  return BA_OK;
+}
+
+int ba_reduced_layout(ba_engine* e, int32_t* n_pad, int32_t* n_full, int32_t* rhs_row) {
+  if (!e) { set_error("null engine"); return BA_ERR_INVALID; }
+  if (n_pad) *n_pad = e->n_pad;
+  if (n_full) *n_full = e->n_full;
+  if (rhs_row) *rhs_row = e->rhs_row;
+  return BA_OK;
+}
+
+int64_t ba_launch_count(void) { return g_launch_count; }
+
+int ba_profile_enable(ba_engine* e, int on) {
+  if (!e) { set_error("null engine"); return BA_ERR_INVALID; }
+  e->profiling = on != 0;
+  return BA_OK;
+}
+
+static int group_id(const char* g) {
+  static const char* names[PG_COUNT] = {"k1", "k2", "k3", "k4", "cost", "other"};
+  for (int i = 0; i < PG_COUNT; ++i)
+    if (g && std::strcmp(g, names[i]) == 0) return i;
+  return -1;
+}
+
+int ba_profile_get(ba_engine* e, const char* group, double* total_ms, int64_t* launches) {
+  const int g = group_id(group);
+  if (!e || g < 0) { set_error("unknown profile group"); return BA_ERR_INVALID; }
+  if (total_ms) *total_ms = e->prof[g].ms;
+  if (launches) *launches = e->prof[g].launches;
+  return BA_OK;
+}
+
+int ba_profile_reset(ba_engine* e) {
+  if (!e) { set_error("null engine"); return BA_ERR_INVALID; }
+  for (int i = 0; i < PG_COUNT; ++i) e->prof[i] = ProfSlot();
+  return BA_OK;
+}
+
+int ba_fp64_peak(int device, int use_dmma, double* tflops) { return fp64_peak(device, use_dmma, tflops); }
+
+}  // extern "C"

@@ -1,0 +1,258 @@
+// K1: per-observation reprojection residuals and analytic Jacobians, plus the cost-only
+// variant and the per-camera derived table they read.
+//
+// Replaces (reference lib/bundle_adjustment.py): _get_K :283-289, _calc_pqr :291-307,
+// _calc_X_diff_pqr :309-322, _calc_f/u/t/R_diff_pqr :324-398, _calc_camera_params_diff_pqr
+// :400-427, the residual terms of _calc_d_P/_calc_d_F :445,:454 and _calc_reprojection_error
+// :666-677.  The reference tiles per-camera rows to (N, M, 3) arrays (:318-320, :368-376);
+// here the per-camera values live in a 128-byte table row staged in shared memory and are
+// never materialised per observation.
+//
+// Memory roofline (HBM): per observation 16 B read (x, y) [+8 B indices when sparse] and
+// 64 B + 160 B written (the point-side and camera-side Jacobian rows, each carrying the
+// residual so that the two consumers stream one row each).
+#include "ba_common.cuh"
+
+namespace ba {
+
+// ---- per-camera derived table -----------------------------------------------------------
+// row: gp(3) gq(3) gr(3) t(3) f u0 v0 pad, with gp = f R[:,0] + u0 R[:,2] etc. = rows of
+// K R^T (:283-302); p = gp . (X - t) reproduces P [X;1] with P[:, 3] = -K R^T t.
+__global__ void cam_prep_kernel(int M, const double* __restrict__ f, const double* __restrict__ u,
+                                const double* __restrict__ R, const double* __restrict__ t,
+                                double f0, double* __restrict__ tab, const ba_lm_state* ctl) {
+  if (ctl && ctl->done) return;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const double fi = f[i], u0 = u[2 * i], v0 = u[2 * i + 1];
+  const double* Ri = R + 9 * i;
+  double* T = tab + (size_t)i * kCamTab;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double r0 = Ri[3 * k + 0], r1 = Ri[3 * k + 1], r2 = Ri[3 * k + 2];
+    T[k] = fi * r0 + u0 * r2;
+    T[3 + k] = fi * r1 + v0 * r2;
+    T[6 + k] = f0 * r2;
+    T[9 + k] = t[3 * i + k];
+  }
+  T[12] = fi;
+  T[13] = u0;
+  T[14] = v0;
+  T[15] = 0.0;
+}
+
+int launch_cam_prep(ba_engine* e, int which, cudaStream_t s) {
+  const CamState& c = e->cam[which];
+  cam_prep_kernel<<<(e->M + 127) / 128, 128, 0, s>>>(e->M, c.f, c.u, c.R, c.t, e->f0,
+                                                      e->camtab[which], nullptr);
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}
+
+struct ObsGeom {
+  double p, q, r, d0, d1, d2;
+};
+
+// ---- K1 -------------------------------------------------------------------------------------
+template <bool DENSE, bool SMEM_TAB>
+__global__ void __launch_bounds__(256)
+k1_residual_jacobian_kernel(int64_t nobs, int M, const int32_t* __restrict__ obs_cam,
+                            const int32_t* __restrict__ obs_pt, const double2* __restrict__ xy,
+                            const double* __restrict__ X, const double* __restrict__ camtab,
+                            double f0, double* __restrict__ JP, double* __restrict__ JC,
+                            double* __restrict__ cost_part, const ba_lm_state* ctl) {
+  if (ctl && (ctl->done || !ctl->need_linearize)) return;
+  extern __shared__ double2 s_tab2[];
+  const double* tab = camtab;
+  if (SMEM_TAB) {
+    const double2* src = reinterpret_cast<const double2*>(camtab);
+    for (int k = threadIdx.x; k < M * (kCamTab / 2); k += blockDim.x) s_tab2[k] = src[k];
+    __syncthreads();
+    tab = reinterpret_cast<const double*>(s_tab2);
+  }
+  __shared__ double scratch[32];
+
+  // contiguous slab of observations per block, 256 at a time (coalesced xy reads)
+  const int64_t per = (nobs + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = per * blockIdx.x;
+  const int64_t hi = lo + per < nobs ? lo + per : nobs;
+  double acc = 0.0;
+  for (int64_t o = lo + threadIdx.x; o < hi; o += blockDim.x) {
+    int i, j;
+    if (DENSE) {
+      j = (int)(o / M);
+      i = (int)(o - (int64_t)j * M);
+    } else {
+      i = obs_cam[o];
+      j = obs_pt[o];
+    }
+    const double* T = tab + (size_t)i * kCamTab;
+    const double gp0 = T[0], gp1 = T[1], gp2 = T[2];
+    const double gq0 = T[3], gq1 = T[4], gq2 = T[5];
+    const double gr0 = T[6], gr1 = T[7], gr2 = T[8];
+    const double fi = T[12], u0 = T[13], v0 = T[14];
+    const double d0 = X[3 * (size_t)j + 0] - T[9];
+    const double d1 = X[3 * (size_t)j + 1] - T[10];
+    const double d2 = X[3 * (size_t)j + 2] - T[11];
+    const double2 m = xy[o];
+
+    const double p = gp0 * d0 + gp1 * d1 + gp2 * d2;
+    const double q = gq0 * d0 + gq1 * d1 + gq2 * d2;
+    const double r = gr0 * d0 + gr1 * d1 + gr2 * d2;
+    const double e0 = p / r - m.x / f0;  // :445
+    const double e1 = q / r - m.y / f0;  // :454
+    acc += e0 * e0 + e1 * e1;
+
+    // a_theta = r dp/dtheta - p dr/dtheta, b_theta = r dq/dtheta - q dr/dtheta; J = (a,b)/r^2
+    const double ir2 = 1.0 / (r * r);
+    const double a0 = r * gp0 - p * gr0, a1 = r * gp1 - p * gr1, a2 = r * gp2 - p * gr2;  // :450
+    const double b0 = r * gq0 - q * gr0, b1 = r * gq1 - q * gr1, b2 = r * gq2 - q * gr2;  // :459
+    const double af = r * ((p - u0 / f0 * r) / fi);  // :336
+    const double bf = r * ((q - v0 / f0 * r) / fi);  // :337
+    const double au = r * (r / f0);                  // :350-356
+    // rotation: d(p,q,r)/dw = grad x (X - t) (:391-396) => a_w = a_X x d, b_w = b_X x d
+    const double aw0 = a1 * d2 - a2 * d1, aw1 = a2 * d0 - a0 * d2, aw2 = a0 * d1 - a1 * d0;
+    const double bw0 = b1 * d2 - b2 * d1, bw1 = b2 * d0 - b0 * d2, bw2 = b0 * d1 - b1 * d0;
+
+    double2* jp = reinterpret_cast<double2*>(JP + (size_t)o * kJP);
+    jp[0] = make_double2(e0, e1);
+    jp[1] = make_double2(a0 * ir2, a1 * ir2);
+    jp[2] = make_double2(a2 * ir2, b0 * ir2);
+    jp[3] = make_double2(b1 * ir2, b2 * ir2);
+
+    double2* jc = reinterpret_cast<double2*>(JC + (size_t)o * kJC);
+    jc[0] = make_double2(e0, e1);
+    // row a: f, u0, v0, t(3) = -a_X (:368-376), w(3)
+    jc[1] = make_double2(af * ir2, au * ir2);
+    jc[2] = make_double2(0.0, -a0 * ir2);
+    jc[3] = make_double2(-a1 * ir2, -a2 * ir2);
+    jc[4] = make_double2(aw0 * ir2, aw1 * ir2);
+    jc[5] = make_double2(aw2 * ir2, bf * ir2);  // end of row a, start of row b
+    jc[6] = make_double2(0.0, au * ir2);
+    jc[7] = make_double2(-b0 * ir2, -b1 * ir2);
+    jc[8] = make_double2(-b2 * ir2, bw0 * ir2);
+    jc[9] = make_double2(bw1 * ir2, bw2 * ir2);
+  }
+  const double tot = block_sum(acc, scratch);
+  if (threadIdx.x == 0) cost_part[blockIdx.x] = tot;
+}
+
+// ---- cost only (:666-677) ---------------------------------------------------------------------
+template <bool DENSE, bool SMEM_TAB>
+__global__ void __launch_bounds__(256)
+cost_kernel(int64_t nobs, int M, const int32_t* __restrict__ obs_cam,
+            const int32_t* __restrict__ obs_pt, const double2* __restrict__ xy,
+            const double* __restrict__ X, const double* __restrict__ camtab, double f0,
+            double* __restrict__ cost_part, const ba_lm_state* ctl) {
+  if (ctl && ctl->done) return;
+  extern __shared__ double2 s_tab2[];
+  const double* tab = camtab;
+  if (SMEM_TAB) {
+    const double2* src = reinterpret_cast<const double2*>(camtab);
+    for (int k = threadIdx.x; k < M * (kCamTab / 2); k += blockDim.x) s_tab2[k] = src[k];
+    __syncthreads();
+    tab = reinterpret_cast<const double*>(s_tab2);
+  }
+  __shared__ double scratch[32];
+  const int64_t per = (nobs + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = per * blockIdx.x;
+  const int64_t hi = lo + per < nobs ? lo + per : nobs;
+  double acc = 0.0;
+  for (int64_t o = lo + threadIdx.x; o < hi; o += blockDim.x) {
+    int i, j;
+    if (DENSE) {
+      j = (int)(o / M);
+      i = (int)(o - (int64_t)j * M);
+    } else {
+      i = obs_cam[o];
+      j = obs_pt[o];
+    }
+    const double* T = tab + (size_t)i * kCamTab;
+    const double d0 = X[3 * (size_t)j + 0] - T[9];
+    const double d1 = X[3 * (size_t)j + 1] - T[10];
+    const double d2 = X[3 * (size_t)j + 2] - T[11];
+    const double2 m = xy[o];
+    const double p = T[0] * d0 + T[1] * d1 + T[2] * d2;
+    const double q = T[3] * d0 + T[4] * d1 + T[5] * d2;
+    const double r = T[6] * d0 + T[7] * d1 + T[8] * d2;
+    const double e0 = p / r - m.x / f0;
+    const double e1 = q / r - m.y / f0;
+    acc += e0 * e0 + e1 * e1;
+  }
+  const double tot = block_sum(acc, scratch);
+  if (threadIdx.x == 0) cost_part[blockIdx.x] = tot;
+}
+
+// Fixed-order final sum of the per-block partials into cost_buf[slot].
+__global__ void cost_finish_kernel(const double* __restrict__ part, int n, double* out,
+                                   const ba_lm_state* ctl, int lin_only) {
+  if (ctl && (ctl->done || (lin_only && !ctl->need_linearize))) return;
+  __shared__ double scratch[32];
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) acc += part[k];
+  const double tot = block_sum(acc, scratch);
+  if (threadIdx.x == 0) *out = tot;
+}
+
+static inline size_t tab_smem_bytes(const ba_engine* e) {
+  const size_t bytes = (size_t)e->M * kCamTab * sizeof(double);
+  return bytes <= 160 * 1024 ? bytes : 0;
+}
+
+int launch_cost(ba_engine* e, int which, int slot, cudaStream_t s) {
+  const size_t smem = tab_smem_bytes(e);
+  const double2* xy = reinterpret_cast<const double2*>(e->obs_xy);
+  const int grid = e->cost_blocks;
+#define BA_COST_LAUNCH(D, T)                                                                   \
+  do {                                                                                         \
+    if (smem > 48 * 1024)                                                                      \
+      BA_CUDA(cudaFuncSetAttribute(cost_kernel<D, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   (int)smem));                                                \
+    cost_kernel<D, T><<<grid, 256, smem, s>>>(e->nobs, e->M, e->obs_cam, e->obs_pt, xy,        \
+                                              e->X[which], e->camtab[which], e->f0,            \
+                                              e->cost_part, nullptr);                          \
+  } while (0)
+  if (e->dense) {
+    if (smem) BA_COST_LAUNCH(true, true); else BA_COST_LAUNCH(true, false);
+  } else {
+    if (smem) BA_COST_LAUNCH(false, true); else BA_COST_LAUNCH(false, false);
+  }
+#undef BA_COST_LAUNCH
+  BA_LAUNCH_CHECK();
+  cost_finish_kernel<<<1, 256, 0, s>>>(e->cost_part, grid, e->cost_buf + slot, nullptr, 0);
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}
+
+int launch_k1(ba_engine* e, cudaStream_t s, bool conditional) {
+  const size_t smem = tab_smem_bytes(e);
+  const double2* xy = reinterpret_cast<const double2*>(e->obs_xy);
+  const int grid = e->cost_blocks;
+  const ba_lm_state* ctl = conditional ? e->ctl : nullptr;
+  // the table of the *current* state must be fresh
+  {
+    const CamState& c = e->cam[0];
+    cam_prep_kernel<<<(e->M + 127) / 128, 128, 0, s>>>(e->M, c.f, c.u, c.R, c.t, e->f0,
+                                                        e->camtab[0], ctl);
+    BA_LAUNCH_CHECK();
+  }
+#define BA_K1_LAUNCH(D, T)                                                                     \
+  do {                                                                                         \
+    if (smem > 48 * 1024)                                                                      \
+      BA_CUDA(cudaFuncSetAttribute(k1_residual_jacobian_kernel<D, T>,                          \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    k1_residual_jacobian_kernel<D, T><<<grid, 256, smem, s>>>(                                 \
+        e->nobs, e->M, e->obs_cam, e->obs_pt, xy, e->X[0], e->camtab[0], e->f0, e->JP, e->JC,  \
+        e->cost_part, ctl);                                                                    \
+  } while (0)
+  if (e->dense) {
+    if (smem) BA_K1_LAUNCH(true, true); else BA_K1_LAUNCH(true, false);
+  } else {
+    if (smem) BA_K1_LAUNCH(false, true); else BA_K1_LAUNCH(false, false);
+  }
+#undef BA_K1_LAUNCH
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}
+
+}  // namespace ba

@@ -1,0 +1,291 @@
+// K2: per-point and per-camera Gauss-Newton blocks.
+//
+//   k2a  V_j = 2 sum_i Jx^T Jx (matE, reference :519-556), g_j = 2 sum_i Jx^T e (d_P, :429-469)
+//        -- one warp per point, warp-level reductions, once per linearisation.
+//   cam  U_i = 2 sum_j Jc^T Jc (diagonal blocks of matG, :618-653), dF_i = 2 sum_j Jc^T e (d_F,
+//        :471-509) -- segmented reduction over the camera-major order, fixed summation order.
+//   k2b  per inner solve: damp V_j (:120-122), Cholesky V_j(1+c) = L L^T instead of the
+//        reference's general inverse (:128), z_j = L^-1 g_j and
+//        Y_ij = W_ij^T L^-T  with W_ij = 2 Jx^T Jc (matF block, :598-605), so that
+//        sum_j F_j^T E_j^-1 F_j = sum_j Y_j Y_j^T (:132-135) becomes a SYRK (K3) and
+//        sum_j F_j^T E_j^-1 d_P_j = sum_j Y_j z_j (:143) rides along as one extra column.
+//
+// Gauge: the 7 removed unknowns (:62-72) are pinned instead of deleted -- their Jc columns are
+// masked here, so the corresponding rows/columns of the reduced system vanish and K4 puts a
+// unit diagonal there (delta = 0, algebraically identical to deletion).
+//
+// Memory roofline (HBM): k2a reads 64 B/obs; cam reads 160 B/obs; k2b reads 64+160 B/obs and
+// writes 216 B/obs (Y).
+#include "ba_common.cuh"
+
+namespace ba {
+
+// ---- k2a --------------------------------------------------------------------------------------
+template <bool DENSE>
+__global__ void __launch_bounds__(256)
+k2a_point_blocks_kernel(int64_t N, int M, const int64_t* __restrict__ obs_ptr,
+                        const double* __restrict__ JP, double* __restrict__ V,
+                        double* __restrict__ GPT, const ba_lm_state* ctl) {
+  if (ctl && (ctl->done || !ctl->need_linearize)) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = warp; j < N; j += nwarps) {
+    const int64_t lo = DENSE ? j * M : obs_ptr[j];
+    const int64_t hi = DENSE ? lo + M : obs_ptr[j + 1];
+    double vxx = 0, vxy = 0, vxz = 0, vyy = 0, vyz = 0, vzz = 0, g0 = 0, g1 = 0, g2 = 0;
+    for (int64_t o = lo + lane; o < hi; o += 32) {
+      const double2* row = reinterpret_cast<const double2*>(JP + (size_t)o * kJP);
+      const double2 r0 = row[0], r1 = row[1], r2 = row[2], r3 = row[3];
+      const double e0 = r0.x, e1 = r0.y;
+      const double a0 = r1.x, a1 = r1.y, a2 = r2.x, b0 = r2.y, b1 = r3.x, b2 = r3.y;
+      vxx += a0 * a0 + b0 * b0;
+      vxy += a0 * a1 + b0 * b1;
+      vxz += a0 * a2 + b0 * b2;
+      vyy += a1 * a1 + b1 * b1;
+      vyz += a1 * a2 + b1 * b2;
+      vzz += a2 * a2 + b2 * b2;
+      g0 += e0 * a0 + e1 * b0;
+      g1 += e0 * a1 + e1 * b1;
+      g2 += e0 * a2 + e1 * b2;
+    }
+    vxx = warp_sum(vxx); vxy = warp_sum(vxy); vxz = warp_sum(vxz);
+    vyy = warp_sum(vyy); vyz = warp_sum(vyz); vzz = warp_sum(vzz);
+    g0 = warp_sum(g0); g1 = warp_sum(g1); g2 = warp_sum(g2);
+    if (lane == 0) {
+      double* v = V + 6 * (size_t)j;
+      v[0] = 2.0 * vxx; v[1] = 2.0 * vxy; v[2] = 2.0 * vxz;
+      v[3] = 2.0 * vyy; v[4] = 2.0 * vyz; v[5] = 2.0 * vzz;
+      double* g = GPT + 3 * (size_t)j;
+      g[0] = 2.0 * g0; g[1] = 2.0 * g1; g[2] = 2.0 * g2;
+    }
+  }
+}
+
+int launch_k2a(ba_engine* e, cudaStream_t s, bool conditional) {
+  const ba_lm_state* ctl = conditional ? e->ctl : nullptr;
+  int64_t blocks = (e->N + 7) / 8;  // 8 warps per block
+  const int64_t cap = (int64_t)e->num_sms * 16;
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  if (e->dense)
+    k2a_point_blocks_kernel<true><<<grid, 256, 0, s>>>(e->N, e->M, e->obs_ptr, e->JP, e->V, e->GPT, ctl);
+  else
+    k2a_point_blocks_kernel<false><<<grid, 256, 0, s>>>(e->N, e->M, e->obs_ptr, e->JP, e->V, e->GPT, ctl);
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}
+
+// ---- camera blocks ----------------------------------------------------------------------------
+// grid (chunks, M); block (i, c) reduces chunk c of camera i's observations into 54 numbers.
+template <bool DENSE>
+__global__ void __launch_bounds__(128)
+camera_blocks_kernel(int64_t N, int M, const int64_t* __restrict__ cam_ptr,
+                     const int32_t* __restrict__ cm_perm, const double* __restrict__ JC,
+                     double* __restrict__ Upart, const ba_lm_state* ctl) {
+  if (ctl && (ctl->done || !ctl->need_linearize)) return;
+  const int i = blockIdx.y;
+  const int chunk = blockIdx.x, nchunks = gridDim.x;
+  const int64_t seg_lo = DENSE ? 0 : cam_ptr[i];
+  const int64_t seg_n = DENSE ? N : cam_ptr[i + 1] - seg_lo;
+  const int64_t per = (seg_n + nchunks - 1) / nchunks;
+  const int64_t lo = per * chunk;
+  const int64_t hi = lo + per < seg_n ? lo + per : seg_n;
+
+  double acc[kUPart];
+#pragma unroll
+  for (int k = 0; k < kUPart; ++k) acc[k] = 0.0;
+  for (int64_t q = lo + threadIdx.x; q < hi; q += blockDim.x) {
+    const int64_t o = DENSE ? q * M + i : (int64_t)cm_perm[seg_lo + q];
+    const double2* row = reinterpret_cast<const double2*>(JC + (size_t)o * kJC);
+    double v[kJC];
+#pragma unroll
+    for (int k = 0; k < kJC / 2; ++k) {
+      const double2 t2 = row[k];
+      v[2 * k] = t2.x;
+      v[2 * k + 1] = t2.y;
+    }
+    const double e0 = v[0], e1 = v[1];
+    const double* a = v + 2;
+    const double* b = v + 11;
+    int idx = 0;
+#pragma unroll
+    for (int r = 0; r < 9; ++r)
+#pragma unroll
+      for (int c = r; c < 9; ++c) acc[idx++] += a[r] * a[c] + b[r] * b[c];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) acc[45 + r] += e0 * a[r] + e1 * b[r];
+  }
+  // block reduction, fixed order: lanes by xor-tree, then warps 0..3 in sequence
+  __shared__ double sred[4][kUPart];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kUPart; ++k) {
+    const double s = warp_sum(acc[k]);
+    if (lane == 0) sred[warp][k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < kUPart) {
+    const double s = ((sred[0][threadIdx.x] + sred[1][threadIdx.x]) + sred[2][threadIdx.x]) +
+                     sred[3][threadIdx.x];
+    Upart[((size_t)i * nchunks + chunk) * kUPart + threadIdx.x] = s;
+  }
+}
+
+// Sum the chunks in order, expand to the full symmetric 9x9, apply factor 2 and the gauge mask.
+__global__ void camera_blocks_finish_kernel(int M, int nchunks, int axis,
+                                            const double* __restrict__ Upart,
+                                            double* __restrict__ U, double* __restrict__ GCAM,
+                                            const ba_lm_state* ctl) {
+  if (ctl && (ctl->done || !ctl->need_linearize)) return;
+  const int i = blockIdx.x;
+  const int k = threadIdx.x;  // 0..89: 81 entries of U, 9 of dF
+  if (k >= 90) return;
+  const uint32_t mask = gauge_mask(i, axis);
+  int src;
+  bool pinned;
+  if (k < 81) {
+    int r = k / 9, c = k % 9;
+    pinned = ((mask >> r) & 1u) || ((mask >> c) & 1u);
+    if (r > c) { int t = r; r = c; c = t; }
+    src = r * 9 - r * (r - 1) / 2 + (c - r);  // index in the packed upper triangle
+  } else {
+    pinned = (mask >> (k - 81)) & 1u;
+    src = 45 + (k - 81);
+  }
+  double s = 0.0;
+  for (int ch = 0; ch < nchunks; ++ch) s += Upart[((size_t)i * nchunks + ch) * kUPart + src];
+  s = pinned ? 0.0 : 2.0 * s;
+  if (k < 81) U[(size_t)i * 81 + k] = s;
+  else GCAM[(size_t)i * 9 + (k - 81)] = s;
+}
+
+int launch_camera_blocks(ba_engine* e, cudaStream_t s, bool conditional) {
+  const ba_lm_state* ctl = conditional ? e->ctl : nullptr;
+  dim3 grid(e->cam_chunks, e->M);
+  if (e->dense)
+    camera_blocks_kernel<true><<<grid, 128, 0, s>>>(e->N, e->M, e->cam_ptr, e->cm_perm, e->JC, e->Upart, ctl);
+  else
+    camera_blocks_kernel<false><<<grid, 128, 0, s>>>(e->N, e->M, e->cam_ptr, e->cm_perm, e->JC, e->Upart, ctl);
+  BA_LAUNCH_CHECK();
+  camera_blocks_finish_kernel<<<e->M, 96, 0, s>>>(e->M, e->cam_chunks, e->axis, e->Upart, e->Uloc,
+                                                   e->Uloc + (size_t)e->M * 81, ctl);
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}
+
+// ---- k2b --------------------------------------------------------------------------------------
+// One warp per point.  Dense layout of Y: Yt[(3j+d) * ld + 9i + a] (k-major operand of the
+// SYRK) with z_j in column rhs_col; sparse layout: Ysp[o][d][a].
+template <bool DENSE>
+__global__ void __launch_bounds__(256)
+k2b_point_solve_kernel(int64_t N, int M, int axis, const int64_t* __restrict__ obs_ptr,
+                       const int32_t* __restrict__ obs_cam, const double* __restrict__ JP,
+                       const double* __restrict__ JC, const double* __restrict__ V,
+                       const double* __restrict__ GPT, double c_host, ba_lm_state* ctl,
+                       int use_ctl, double* __restrict__ LINV, double* __restrict__ Z,
+                       double* __restrict__ Yt, int ld, int rhs_col, double* __restrict__ Ysp) {
+  if (use_ctl && ctl->done) return;
+  const double c = use_ctl ? ctl->c : c_host;
+  const double damp = 1.0 + c;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = warp; j < N; j += nwarps) {
+    const double* v = V + 6 * (size_t)j;
+    // damped block (:120-122) and its Cholesky factor
+    const double vxx = v[0] * damp, vxy = v[1], vxz = v[2], vyy = v[3] * damp, vyz = v[4],
+                 vzz = v[5] * damp;
+    const double l00 = sqrt(vxx);
+    const double l10 = vxy / l00, l20 = vxz / l00;
+    const double d11 = vyy - l10 * l10;
+    const double l11 = sqrt(d11);
+    const double l21 = (vyz - l20 * l10) / l11;
+    const double d22 = vzz - l20 * l20 - l21 * l21;
+    const double l22 = sqrt(d22);
+    if (!(vxx > 0.0) || !(d11 > 0.0) || !(d22 > 0.0)) {
+      // singular / indefinite point block: the reference's inv() raises LinAlgError (:128)
+      if (lane == 0) atomicExch(&ctl->status, (int)BA_ERR_SINGULAR);
+    }
+    // inverse of L (lower): m = L^-1
+    const double m00 = 1.0 / l00, m11 = 1.0 / l11, m22 = 1.0 / l22;
+    const double m10 = -l10 * m00 * m11;
+    const double m21 = -l21 * m11 * m22;
+    const double m20 = -(l20 * m00 + l21 * m10) * m22;
+    const double* g = GPT + 3 * (size_t)j;
+    const double z0 = m00 * g[0];
+    const double z1 = m10 * g[0] + m11 * g[1];
+    const double z2 = m20 * g[0] + m21 * g[1] + m22 * g[2];
+    if (lane == 0) {
+      double* li = LINV + 6 * (size_t)j;
+      li[0] = m00; li[1] = m10; li[2] = m11; li[3] = m20; li[4] = m21; li[5] = m22;
+      double* z = Z + 3 * (size_t)j;
+      z[0] = z0; z[1] = z1; z[2] = z2;
+      if (DENSE) {
+        Yt[(size_t)(3 * j + 0) * ld + rhs_col] = z0;
+        Yt[(size_t)(3 * j + 1) * ld + rhs_col] = z1;
+        Yt[(size_t)(3 * j + 2) * ld + rhs_col] = z2;
+      }
+    }
+    const int64_t lo = DENSE ? j * M : obs_ptr[j];
+    const int64_t hi = DENSE ? lo + M : obs_ptr[j + 1];
+    for (int64_t o = lo + lane; o < hi; o += 32) {
+      const int i = DENSE ? (int)(o - lo) : obs_cam[o];
+      const uint32_t mask = gauge_mask(i, axis);
+      const double2* rp = reinterpret_cast<const double2*>(JP + (size_t)o * kJP);
+      const double2 p1 = rp[1], p2 = rp[2], p3 = rp[3];
+      const double a0 = p1.x, a1 = p1.y, a2 = p2.x, b0 = p2.y, b1 = p3.x, b2 = p3.y;
+      // T = 2 Jx L^-T  (2x3): T[k][d] = 2 sum_b Jx[k][b] m[d][b]
+      const double ta0 = 2.0 * (a0 * m00), ta1 = 2.0 * (a0 * m10 + a1 * m11),
+                   ta2 = 2.0 * (a0 * m20 + a1 * m21 + a2 * m22);
+      const double tb0 = 2.0 * (b0 * m00), tb1 = 2.0 * (b0 * m10 + b1 * m11),
+                   tb2 = 2.0 * (b0 * m20 + b1 * m21 + b2 * m22);
+      const double2* rc = reinterpret_cast<const double2*>(JC + (size_t)o * kJC);
+      double jc[kJC];
+#pragma unroll
+      for (int k = 1; k < kJC / 2; ++k) {
+        const double2 t2 = rc[k];
+        jc[2 * k] = t2.x;
+        jc[2 * k + 1] = t2.y;
+      }
+      // Y[a][d] = Jc0[a] T[0][d] + Jc1[a] T[1][d]
+#pragma unroll
+      for (int a = 0; a < 9; ++a) {
+        const bool pin = (mask >> a) & 1u;
+        const double ja = pin ? 0.0 : jc[2 + a], jb = pin ? 0.0 : jc[11 + a];
+        const double y0 = ja * ta0 + jb * tb0;
+        const double y1 = ja * ta1 + jb * tb1;
+        const double y2 = ja * ta2 + jb * tb2;
+        if (DENSE) {
+          const size_t col = 9 * (size_t)i + a;
+          Yt[(size_t)(3 * j + 0) * ld + col] = y0;
+          Yt[(size_t)(3 * j + 1) * ld + col] = y1;
+          Yt[(size_t)(3 * j + 2) * ld + col] = y2;
+        } else {
+          double* y = Ysp + (size_t)o * 27;
+          y[a] = y0;
+          y[9 + a] = y1;
+          y[18 + a] = y2;
+        }
+      }
+    }
+  }
+}
+
+int launch_k2b(ba_engine* e, bool conditional, double c_host, cudaStream_t s) {
+  const int use_ctl = conditional ? 1 : 0;
+  int64_t blocks = (e->N + 7) / 8;
+  const int64_t cap = (int64_t)e->num_sms * 16;
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  if (e->dense)
+    k2b_point_solve_kernel<true><<<grid, 256, 0, s>>>(
+        e->N, e->M, e->axis, e->obs_ptr, e->obs_cam, e->JP, e->JC, e->V, e->GPT, c_host, e->ctl,
+        use_ctl, e->LINV, e->Z, e->Yt, e->n_pad, e->rhs_row, e->Ysp);
+  else
+    k2b_point_solve_kernel<false><<<grid, 256, 0, s>>>(
+        e->N, e->M, e->axis, e->obs_ptr, e->obs_cam, e->JP, e->JC, e->V, e->GPT, c_host, e->ctl,
+        use_ctl, e->LINV, e->Z, e->Yt, e->n_pad, e->rhs_row, e->Ysp);
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}
+
+}  // namespace ba

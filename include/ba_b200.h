@@ -1,0 +1,194 @@
+/*
+ * ba_b200.h -- C ABI of the B200-native bundle-adjustment engine (libba_b200.so).
+ *
+ * Drop-in boundary for the perspective-camera Levenberg-Marquardt refinement of the reference
+ * repository takah29/3d-reconstruction-from-multi-view-exp, file lib/bundle_adjustment.py
+ * (class BundleAdjuster).  The reference is pure Python and has no FFI of its own; these are
+ * the entry points a binding for that class needs (last row), and each
+ * one cites the reference lines it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain C types only; every array is float64 unless stated; the caller owns all buffers;
+ *   - `mem` says where the caller's buffers live: BA_MEM_HOST or BA_MEM_DEVICE (a raw device
+ *     pointer, e.g. torch.Tensor.data_ptr());
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work of
+ *     a call is enqueued on it; calls that return values to host memory synchronise it;
+ *   - every function returns a ba_status; ba_last_error() gives the message of the last
+ *     failure on the calling thread;
+ *   - state is held in the *normalised gauge frame* of the reference (camera 0 = identity at
+ *     the origin, baseline component = +-1; lib/bundle_adjustment.py:208-240).  The O(N)
+ *     normalise / denormalise steps stay on the host side of the boundary.
+ *   - one engine per process and GPU.  Points may be sharded over several engines (one per
+ *     rank); the camera block is replicated and the host all-reduces two device buffers per
+ *     inner solve (ba_reduce_buffer / ba_cost_buffer) -- see the phase functions below.
+ */
+#ifndef BA_B200_H
+#define BA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BA_B200_VERSION 1
+
+typedef struct ba_engine ba_engine;
+
+typedef enum ba_status {
+  BA_OK = 0,
+  BA_ERR_INVALID = 1,   /* bad argument            -> ValueError   (reference :28, :232)   */
+  BA_ERR_CUDA = 2,      /* CUDA runtime failure     -> RuntimeError                         */
+  BA_ERR_SINGULAR = 3,  /* singular point block     -> LinAlgError  (reference :128, :146)  */
+  BA_ERR_STATE = 4,     /* call out of order        -> RuntimeError                         */
+  BA_ERR_NO_DEVICE = 5, /* no CUDA device           -> RuntimeError (there is no CPU path)  */
+  BA_ERR_STALL = 6      /* inner LM loop exceeded max_retries -> RuntimeError (the reference
+                           loops forever, :118; documented deviation)                       */
+} ba_status;
+
+enum { BA_MEM_HOST = 0, BA_MEM_DEVICE = 1 };
+enum { BA_AXIS_X_RIGHT = 0, BA_AXIS_X_UP = 1 }; /* reference :23-33, :62-72 */
+enum { BA_STATE_CURRENT = 0, BA_STATE_TRIAL = 1 };
+
+/* Problem description (constructor arguments of the reference class, :11-21, in
+ * observation-list form). */
+typedef struct ba_problem {
+  int64_t n_points;     /* points owned by this engine (a shard of the scene)                */
+  int64_t n_obs;        /* visible (point, camera) pairs of those points                     */
+  int32_t n_cams;       /* cameras (all of them; replicated on every shard)                  */
+  int32_t axis;         /* BA_AXIS_*: which baseline component the gauge pins                */
+  double f0;            /* image-coordinate scale (reference :18, :50)                       */
+  int32_t dense;        /* 1: every point sees every camera, obs o = point*n_cams + camera   */
+  int32_t device;       /* CUDA device ordinal                                               */
+} ba_problem;
+
+/* Levenberg-Marquardt control block, mirrored from device memory (reference :100-195). */
+typedef struct ba_lm_state {
+  double E;             /* cost of the current (accepted) state                              */
+  double E_trial;       /* cost of the last trial state                                      */
+  double c;             /* Marquardt damping factor (:100, :165, :195)                       */
+  double delta;         /* |E_trial - E| of the last accepted iteration (:186)               */
+  double scale_factor;  /* :79                                                               */
+  double delta_tol;     /* :80                                                               */
+  int32_t count;        /* accepted iterations so far (:185)                                 */
+  int32_t max_iter;     /* :81                                                               */
+  int32_t solves;       /* inner solves so far                                               */
+  int32_t iter_solves;  /* inner solves of the iteration in progress                         */
+  int32_t need_linearize; /* 1: next solve re-linearises (after an accept)                   */
+  int32_t accepted;     /* 1: the last decide() accepted the trial                           */
+  int32_t done;         /* 1: terminated (:191)                                              */
+  int32_t status;       /* ba_status raised on the device (singular block, stall)            */
+  int32_t chol_fail;    /* 1: last reduced system was not positive definite (step rejected)  */
+  int32_t max_retries;  /* cap on inner solves per iteration                                 */
+} ba_lm_state;
+
+/* One record per accepted iteration (what the reference prints and logs, :175-188). */
+typedef struct ba_iter_record {
+  double E_prev;
+  double E;
+  double delta;
+  double c;
+  int32_t solves;
+  int32_t count;
+} ba_iter_record;
+
+/* ---- life cycle ------------------------------------------------------------------- */
+int ba_version(void);
+const char* ba_last_error(void);
+int ba_device_count(void);
+/* BundleAdjuster.__init__ (:11-75) after host-side gauge normalisation. */
+int ba_create(const ba_problem* problem, ba_engine** out);
+int ba_destroy(ba_engine* e);
+
+/* Observations (:36-37, :56-60) as CSR by point: obs_ptr[n_points+1], obs_cam[n_obs] (may be
+ * NULL when problem.dense), obs_xy[n_obs][2].  Builds the camera-major index on the device. */
+int ba_set_observations(ba_engine* e, const int64_t* obs_ptr, const int32_t* obs_cam,
+                        const double* obs_xy, int mem, void* stream);
+/* State in the normalised frame: X[n_points][3], R[n_cams][3][3], t[n_cams][3], f[n_cams],
+ * u[n_cams][2]  (:40-48).  Any pointer may be NULL to leave that part untouched. */
+int ba_set_state(ba_engine* e, const double* X, const double* R, const double* t,
+                 const double* f, const double* u, int mem, void* stream);
+int ba_get_state(ba_engine* e, int which, double* X, double* R, double* t, double* f, double* u,
+                 int mem, void* stream);
+
+/* ---- single kernels / phases (each cites what it replaces) --------------------------- */
+/* _calc_reprojection_error (:666-677): local cost of the current state into the cost buffer
+ * slot 0 (a partial sum when the scene is sharded). */
+int ba_cost(ba_engine* e, int which, void* stream);
+/* K1 + per-point and per-camera reductions: _calc_pqr, _calc_*_diff_pqr, _calc_d_P, _calc_d_F,
+ * _calc_matE, _calc_matG (:103-116).  Unconditional. */
+int ba_linearize(ba_engine* e, void* stream);
+/* K2 + K3 for damping `c`: damp/invert V_j, Y_j, partial Schur products into the reduce
+ * buffer (:120-143).  Unconditional. */
+int ba_build_reduced(ba_engine* e, double c, void* stream);
+/* K4 for damping `c` on the (all-reduced) reduce buffer: assemble, Cholesky, solve,
+ * back-substitute, trial state and its local cost (:146-162).  Unconditional. */
+int ba_solve_trial(ba_engine* e, double c, void* stream);
+
+/* ---- the LM loop with its control flow on the device --------------------------------- */
+/* optimize() prologue (:85-101): reset the control block, cost of the initial state. */
+int ba_lm_begin(ba_engine* e, double scale_factor, double delta_tol, int max_iter,
+                int max_retries, void* stream);
+/* Phase 1 of an inner solve: (re-)linearise if flagged, build the partial reduced system.
+ * Sharded runs all-reduce ba_reduce_buffer() afterwards. */
+int ba_lm_phase_reduce(ba_engine* e, void* stream);
+/* Phase 2: solve, trial state, local trial cost.  Sharded runs all-reduce ba_cost_buffer(). */
+int ba_lm_phase_solve(ba_engine* e, void* stream);
+/* Phase 3: accept / reject, damping schedule, termination (:164-195); commits the trial. */
+int ba_lm_phase_decide(ba_engine* e, void* stream);
+/* Copy the control block to the host (synchronises `stream`). */
+int ba_lm_state_get(ba_engine* e, ba_lm_state* out, void* stream);
+/* Run inner solves until one iteration is accepted or the loop terminates (single engine). */
+int ba_lm_iterate(ba_engine* e, ba_lm_state* out, void* stream);
+/* Whole optimize() loop (:102-195) for a single engine; records[0..*n_records) receive one
+ * entry per accepted iteration (at most max_records). */
+int ba_lm_run(ba_engine* e, double scale_factor, double delta_tol, int max_iter, int max_retries,
+              ba_iter_record* records, int max_records, int* n_records, ba_lm_state* final_state,
+              void* stream);
+int ba_lm_records(ba_engine* e, ba_iter_record* records, int max_records, int* n_records,
+                  void* stream);
+
+/* ---- buffers the host all-reduces when points are sharded over ranks ----------------- */
+/* Partial reduced system: [P (n_pad x n_pad) | U (n_cams x 81) | dF (n_cams x 9)] doubles. */
+int ba_reduce_buffer(ba_engine* e, void** device_ptr, int64_t* n_doubles);
+/* [cost slot 0 (current / initial), cost slot 1 (trial)] doubles. */
+int ba_cost_buffer(ba_engine* e, void** device_ptr, int64_t* n_doubles);
+/* Only one rank prints/logs; every rank must still hold the same U/dF: this marks whether
+ * this engine's U/dF partials are to be counted (all ranks: 1). */
+
+/* ---- inspection (tests, ncu-free evidence); copies to host memory ------------------- */
+typedef enum ba_buffer_id {
+  BA_BUF_JP = 0,     /* [n_obs][8]  e0,e1, d e/dX (2x3)                    K1   */
+  BA_BUF_JC = 1,     /* [n_obs][20] e0,e1, d e/d(f,u0,v0,t,w) (2x9)       K1   */
+  BA_BUF_V = 2,      /* [n_points][6] xx,xy,xz,yy,yz,zz of matE (:519)     K2   */
+  BA_BUF_GPT = 3,    /* [n_points][3] d_P (:429)                           K2   */
+  BA_BUF_U = 4,      /* [n_cams][81] diagonal blocks of matG (:618), gauge rows zeroed */
+  BA_BUF_GCAM = 5,   /* [n_cams][9]  d_F (:471), gauge entries zeroed            */
+  BA_BUF_S = 6,      /* [n_pad][n_pad] reduced system after assembly / Cholesky (lower) */
+  BA_BUF_DXI = 7,    /* [n_cams][9] camera step, zeros at the gauge entries (:146, :267) */
+  BA_BUF_LINV = 8,   /* [n_points][6] inverse Cholesky factor of damped V_j     K2 */
+  BA_BUF_Z = 9,      /* [n_points][3] L_j^-1 d_P_j                               K2 */
+  BA_BUF_REDUCE = 10,/* the reduce buffer (see ba_reduce_buffer)                    */
+  BA_BUF_COST = 11   /* [2] cost of the current / initial state, cost of the trial  */
+} ba_buffer_id;
+int ba_buffer_size(ba_engine* e, int id, int64_t* n_doubles);
+int ba_buffer_read(ba_engine* e, int id, double* host_out, int64_t n_doubles, void* stream);
+/* Layout facts the host needs: padded order of the reduced system and its rhs row. */
+int ba_reduced_layout(ba_engine* e, int32_t* n_pad, int32_t* n_full, int32_t* rhs_row);
+
+/* ---- profiling helpers ------------------------------------------------------------ */
+/* Number of kernels this library launched since ba_create (all engines of the process). */
+int64_t ba_launch_count(void);
+/* Device time (ms, CUDA events on `stream`) and launches of the named kernel group
+ * accumulated while profiling is enabled; groups: "k1","k2","k3","k4","cost","other". */
+int ba_profile_enable(ba_engine* e, int on);
+int ba_profile_get(ba_engine* e, const char* group, double* total_ms, int64_t* launches);
+int ba_profile_reset(ba_engine* e);
+/* FP64 peak micro-benchmarks (register-resident DMMA.8x8x4 / DFMA loops): TFLOP/s. */
+int ba_fp64_peak(int device, int use_dmma, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BA_B200_H */
