@@ -57,7 +57,9 @@ struct CamState {
   double* t = nullptr;  // [M][3]
 };
 
-enum ProfGroup { PG_K1 = 0, PG_K2, PG_K3, PG_K4, PG_COST, PG_OTHER, PG_COUNT };
+// "k3" brackets the whole Schur phase; "syrk" only the DMMA kernel inside it (nested scopes
+// use their own event pair).
+enum ProfGroup { PG_K1 = 0, PG_K2, PG_K3, PG_K4, PG_COST, PG_OTHER, PG_SYRK, PG_CHOL, PG_COUNT };
 
 struct ProfSlot {
   double ms = 0.0;
@@ -138,18 +140,25 @@ struct ProfScope {
   int group;
   cudaStream_t s;
   int64_t launches_before;
+  cudaEvent_t a = nullptr, b = nullptr;  // own pair: scopes may nest
   ProfScope(ba_engine* e_, int group_, cudaStream_t s_) : e(e_), group(group_), s(s_) {
     launches_before = g_launch_count;
-    if (e->profiling) cudaEventRecord(e->ev0, s);
+    if (e->profiling) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, s);
+    }
   }
   ~ProfScope() {
     e->prof[group].launches += g_launch_count - launches_before;
-    if (e->profiling) {
-      cudaEventRecord(e->ev1, s);
-      cudaEventSynchronize(e->ev1);
+    if (a) {
+      cudaEventRecord(b, s);
+      cudaEventSynchronize(b);
       float ms = 0.f;
-      cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+      cudaEventElapsedTime(&ms, a, b);
       e->prof[group].ms += ms;
+      cudaEventDestroy(a);
+      cudaEventDestroy(b);
     }
   }
 };

@@ -271,7 +271,7 @@ static int phase_reduce(ba_engine* e, bool conditional, double c_host, cudaStrea
 static int phase_solve(ba_engine* e, bool conditional, double c_host, cudaStream_t s) {
   ProfScope ps(e, PG_K4, s);
   BA_TRY(launch_assemble(e, conditional, c_host, s));
-  BA_TRY(launch_cholesky_solve(e, conditional, s));
+  { ProfScope pc(e, PG_CHOL, s); BA_TRY(launch_cholesky_solve(e, conditional, s)); }
   BA_TRY(launch_update_trial(e, conditional, s));
   return BA_OK;
 }
@@ -567,7 +567,7 @@ int ba_profile_enable(ba_engine* e, int on) {
 }
 
 static int group_id(const char* g) {
-  static const char* names[PG_COUNT] = {"k1", "k2", "k3", "k4", "cost", "other"};
+  static const char* names[PG_COUNT] = {"k1", "k2", "k3", "k4", "cost", "other", "syrk", "chol"};
   for (int i = 0; i < PG_COUNT; ++i)
     if (g && std::strcmp(g, names[i]) == 0) return i;
   return -1;

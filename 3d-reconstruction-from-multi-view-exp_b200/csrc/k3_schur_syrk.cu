@@ -229,9 +229,12 @@ static int launch_syrk(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
   BA_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<TILE, WR, WC>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(n_tiles, splits);
-  syrk_dmma_kernel<TILE, WR, WC><<<grid, WR * WC * 32, smem, s>>>(e->Yt, e->n_pad, n_chunks, cps,
-                                                                 n_tiles, e->Spart, ctl);
-  BA_LAUNCH_CHECK();
+  {
+    ProfScope ps(e, PG_SYRK, s);
+    syrk_dmma_kernel<TILE, WR, WC><<<grid, WR * WC * 32, smem, s>>>(e->Yt, e->n_pad, n_chunks, cps,
+                                                                   n_tiles, e->Spart, ctl);
+    BA_LAUNCH_CHECK();
+  }
   syrk_reduce_kernel<TILE><<<n_tiles, 256, 0, s>>>(e->Spart, n_tiles, splits, e->P(), e->n_pad, ctl);
   BA_LAUNCH_CHECK();
   return BA_OK;

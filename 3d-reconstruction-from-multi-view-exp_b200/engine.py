@@ -202,7 +202,7 @@ class Engine:
 
     def profile(self) -> dict:
         out = {}
-        for g in ("k1", "k2", "k3", "k4", "cost", "other"):
+        for g in ("k1", "k2", "k3", "k4", "cost", "other", "syrk", "chol"):
             ms, n = C.c_double(), C.c_int64()
             _cabi.check(self._lib.ba_profile_get(self._h, g.encode(), C.byref(ms), C.byref(n)))
             out[g] = {"ms": ms.value, "launches": n.value}

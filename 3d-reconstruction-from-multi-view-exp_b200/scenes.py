@@ -124,15 +124,24 @@ def make_scene(
     min_views: int = 3,
     axis: str = "x-up_z-forward",
     chunk: int = 20000,
+    point_stream: int = 0,
 ) -> Scene:
-    rs = np.random.RandomState(seed)
+    """`seed` fixes the cameras (ground truth and initial perturbation); the points, their
+    visibility and the image noise come from a second stream keyed by (`seed`,
+    `point_stream`), so that the ranks of a sharded run share the cameras and draw disjoint
+    point shards (`point_stream = rank`)."""
+    rs_cam = np.random.RandomState(seed)
     f0 = 1.0
-    pos = hemisphere_positions(rs, n_cams, 5.0)
-    targets = rs.normal(0, 0.5, (n_cams, 3))
+    pos = hemisphere_positions(rs_cam, n_cams, 5.0)
+    targets = rs_cam.normal(0, 0.5, (n_cams, 3))
     R_gt = look_at(pos, targets)
     t_gt = pos
     f_gt = np.ones(n_cams)
     u_gt = np.zeros((n_cams, 2))
+    t0 = t_gt + perturb * rs_cam.standard_normal(t_gt.shape)
+    R0 = rodrigues_batch(perturb * rs_cam.standard_normal((n_cams, 3))) @ R_gt
+
+    rs = np.random.RandomState((seed * 7919 + 104729 * (point_stream + 1)) % (2**31 - 1))
     X_gt = rs.uniform(-1, 1, (n_points, 3))
 
     dense = visibility >= 1.0
@@ -167,8 +176,6 @@ def make_scene(
 
     # perturbed-ground-truth initial value
     X0 = X_gt + perturb * rs.standard_normal(X_gt.shape)
-    t0 = t_gt + perturb * rs.standard_normal(t_gt.shape)
-    R0 = rodrigues_batch(perturb * rs.standard_normal((n_cams, 3))) @ R_gt
     K_gt = np.zeros((n_cams, 3, 3))
     K_gt[:, 0, 0] = K_gt[:, 1, 1] = f_gt
     K_gt[:, 2, 2] = f0

@@ -181,7 +181,8 @@ int ba_reduced_layout(ba_engine* e, int32_t* n_pad, int32_t* n_full, int32_t* rh
 /* Number of kernels this library launched since ba_create (all engines of the process). */
 int64_t ba_launch_count(void);
 /* Device time (ms, CUDA events on `stream`) and launches of the named kernel group
- * accumulated while profiling is enabled; groups: "k1","k2","k3","k4","cost","other". */
+ * accumulated while profiling is enabled; groups: "k1","k2","k3","k4","cost","other", and
+ * nested inside k3 / k4: "syrk" (the DMMA kernel alone), "chol" (factor + solve). */
 int ba_profile_enable(ba_engine* e, int on);
 int ba_profile_get(ba_engine* e, const char* group, double* total_ms, int64_t* launches);
 int ba_profile_reset(ba_engine* e);
