@@ -111,6 +111,7 @@ struct ba_engine {
   int64_t red_len = 0;
   double* Spart = nullptr;  // split-K partial tiles
   double* Lt = nullptr;     // Cholesky panel, k-major copy [kCholNB][n_pad]
+  double* Winv = nullptr;   // [panels][64][64] L_D^-T of every diagonal block (back substitution)
   double* dxi = nullptr;    // [M][9]
   double* cost_part = nullptr;
   int cost_blocks = 0;

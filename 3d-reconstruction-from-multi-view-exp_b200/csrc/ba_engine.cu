@@ -110,7 +110,7 @@ static void free_engine(ba_engine* e) {
   cudaSetDevice(e->device);
   void* ptrs[] = {e->obs_ptr, e->obs_cam, e->obs_pt, e->obs_xy, e->cam_ptr, e->cm_perm, e->X[0],
                   e->X[1], e->cam[0].f, e->cam[1].f, e->camtab[0], e->camtab[1], e->JP, e->JC, e->V,
-                  e->GPT, e->Upart, e->Uloc, e->LINV, e->Z, e->Yt, e->Ysp, e->red, e->Spart, e->Lt,
+                  e->GPT, e->Upart, e->Uloc, e->LINV, e->Z, e->Yt, e->Ysp, e->red, e->Spart, e->Lt, e->Winv,
                   e->dxi, e->cost_part, e->cost_buf, e->ctl, e->rec};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -167,8 +167,8 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
   e->rhs_row = e->n_full;
   const int n_aug = e->n_full + 1;
   e->syrk_tile = n_aug <= 1024 ? 64 : 128;
-  e->n_pad = round_up(n_aug, e->syrk_tile);
-  e->k_pad = round_up64(3 * e->N, 16);
+  e->n_pad = round_up(n_aug, 8);  // fragment granularity; edge tiles of the SYRK are partial
+  e->k_pad = round_up64(3 * e->N, 32);
   e->syrk_splits = syrk_choose_splits(e->n_pad, e->syrk_tile, e->k_pad, e->num_sms);
   e->cam_chunks = (4 * e->num_sms + e->M - 1) / e->M;
   if (e->cam_chunks < 1) e->cam_chunks = 1;
@@ -210,12 +210,13 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
   A(dev_alloc(&e->red, (size_t)e->red_len));
   if (e->dense) {
     A(dev_alloc(&e->Yt, (size_t)e->k_pad * e->n_pad));
-    const int nt1 = e->n_pad / e->syrk_tile;
+    const int nt1 = (e->n_pad + e->syrk_tile - 1) / e->syrk_tile;
     A(dev_alloc(&e->Spart, (size_t)e->syrk_splits * (nt1 * (nt1 + 1) / 2) * e->syrk_tile * e->syrk_tile));
   } else {
     A(dev_alloc(&e->Ysp, (size_t)e->nobs * 27));
   }
   A(dev_alloc(&e->Lt, (size_t)kCholNB * e->n_pad));
+  A(dev_alloc(&e->Winv, (size_t)((e->n_full + kCholNB - 1) / kCholNB) * kCholNB * kCholNB));
   A(dev_alloc(&e->dxi, (size_t)e->n_full));
   A(dev_alloc(&e->cost_part, (size_t)e->num_sms * 16 + 1024));
   A(dev_alloc(&e->cost_buf, (size_t)2));

@@ -49,9 +49,7 @@ int launch_cam_prep(ba_engine* e, int which, cudaStream_t s) {
   return BA_OK;
 }
 
-struct ObsGeom {
-  double p, q, r, d0, d1, d2;
-};
+constexpr int kK1Stage = 32 * 29;  // staging doubles per warp
 
 // ---- K1 -------------------------------------------------------------------------------------
 template <bool DENSE, bool SMEM_TAB>
@@ -71,13 +69,21 @@ k1_residual_jacobian_kernel(int64_t nobs, int M, const int32_t* __restrict__ obs
     tab = reinterpret_cast<const double*>(s_tab2);
   }
   __shared__ double scratch[32];
+  // per-warp staging of the 32 x (8 + 20) output doubles (row stride 29: conflict-free), so the
+  // Jacobian rows leave the SM as whole contiguous runs instead of per-lane 16-byte pieces
+  const int lane = threadIdx.x & 31;
+  double* st = reinterpret_cast<double*>(s_tab2) + (SMEM_TAB ? (size_t)M * kCamTab : 0) +
+               (size_t)(threadIdx.x >> 5) * kK1Stage;
 
   // contiguous slab of observations per block, 256 at a time (coalesced xy reads)
   const int64_t per = (nobs + gridDim.x - 1) / gridDim.x;
   const int64_t lo = per * blockIdx.x;
   const int64_t hi = lo + per < nobs ? lo + per : nobs;
   double acc = 0.0;
-  for (int64_t o = lo + threadIdx.x; o < hi; o += blockDim.x) {
+  for (int64_t o0 = lo + (threadIdx.x & ~31); o0 < hi; o0 += blockDim.x) {
+    const int64_t o = o0 + lane;
+    const int cnt = (int)(hi - o0 < 32 ? hi - o0 : 32);
+    if (o < hi) {
     int i, j;
     if (DENSE) {
       j = (int)(o / M);
@@ -114,24 +120,30 @@ k1_residual_jacobian_kernel(int64_t nobs, int M, const int32_t* __restrict__ obs
     const double aw0 = a1 * d2 - a2 * d1, aw1 = a2 * d0 - a0 * d2, aw2 = a0 * d1 - a1 * d0;
     const double bw0 = b1 * d2 - b2 * d1, bw1 = b2 * d0 - b0 * d2, bw2 = b0 * d1 - b1 * d0;
 
-    double2* jp = reinterpret_cast<double2*>(JP + (size_t)o * kJP);
-    jp[0] = make_double2(e0, e1);
-    jp[1] = make_double2(a0 * ir2, a1 * ir2);
-    jp[2] = make_double2(a2 * ir2, b0 * ir2);
-    jp[3] = make_double2(b1 * ir2, b2 * ir2);
-
-    double2* jc = reinterpret_cast<double2*>(JC + (size_t)o * kJC);
-    jc[0] = make_double2(e0, e1);
-    // row a: f, u0, v0, t(3) = -a_X (:368-376), w(3)
-    jc[1] = make_double2(af * ir2, au * ir2);
-    jc[2] = make_double2(0.0, -a0 * ir2);
-    jc[3] = make_double2(-a1 * ir2, -a2 * ir2);
-    jc[4] = make_double2(aw0 * ir2, aw1 * ir2);
-    jc[5] = make_double2(aw2 * ir2, bf * ir2);  // end of row a, start of row b
-    jc[6] = make_double2(0.0, au * ir2);
-    jc[7] = make_double2(-b0 * ir2, -b1 * ir2);
-    jc[8] = make_double2(-b2 * ir2, bw0 * ir2);
-    jc[9] = make_double2(bw1 * ir2, bw2 * ir2);
+    double* w = st + lane * 29;
+    w[0] = e0; w[1] = e1;
+    w[2] = a0 * ir2; w[3] = a1 * ir2; w[4] = a2 * ir2;
+    w[5] = b0 * ir2; w[6] = b1 * ir2; w[7] = b2 * ir2;
+    // camera row: e, then row a: f, u0, v0, t(3) = -a_X (:368-376), w(3); row b likewise
+    w[8] = e0; w[9] = e1;
+    w[10] = af * ir2; w[11] = au * ir2; w[12] = 0.0;
+    w[13] = -a0 * ir2; w[14] = -a1 * ir2; w[15] = -a2 * ir2;
+    w[16] = aw0 * ir2; w[17] = aw1 * ir2; w[18] = aw2 * ir2;
+    w[19] = bf * ir2; w[20] = 0.0; w[21] = au * ir2;
+    w[22] = -b0 * ir2; w[23] = -b1 * ir2; w[24] = -b2 * ir2;
+    w[25] = bw0 * ir2; w[26] = bw1 * ir2; w[27] = bw2 * ir2;
+    }
+    __syncwarp();
+    {
+      double* dp = JP + (size_t)o0 * kJP;
+      for (int k = lane; k < kJP * cnt; k += 32) dp[k] = st[(k >> 3) * 29 + (k & 7)];
+      double* dc = JC + (size_t)o0 * kJC;
+      for (int k = lane; k < kJC * cnt; k += 32) {
+        const int row = k / kJC;
+        dc[k] = st[row * 29 + 8 + (k - row * kJC)];
+      }
+    }
+    __syncwarp();
   }
   const double tot = block_sum(acc, scratch);
   if (threadIdx.x == 0) cost_part[blockIdx.x] = tot;
@@ -225,7 +237,8 @@ int launch_cost(ba_engine* e, int which, int slot, cudaStream_t s) {
 }
 
 int launch_k1(ba_engine* e, cudaStream_t s, bool conditional) {
-  const size_t smem = tab_smem_bytes(e);
+  const size_t tab_bytes = tab_smem_bytes(e);
+  const size_t smem = tab_bytes + 8 * kK1Stage * sizeof(double);
   const double2* xy = reinterpret_cast<const double2*>(e->obs_xy);
   const int grid = e->cost_blocks;
   const ba_lm_state* ctl = conditional ? e->ctl : nullptr;
@@ -246,9 +259,9 @@ int launch_k1(ba_engine* e, cudaStream_t s, bool conditional) {
         e->cost_part, ctl);                                                                    \
   } while (0)
   if (e->dense) {
-    if (smem) BA_K1_LAUNCH(true, true); else BA_K1_LAUNCH(true, false);
+    if (tab_bytes) BA_K1_LAUNCH(true, true); else BA_K1_LAUNCH(true, false);
   } else {
-    if (smem) BA_K1_LAUNCH(false, true); else BA_K1_LAUNCH(false, false);
+    if (tab_bytes) BA_K1_LAUNCH(false, true); else BA_K1_LAUNCH(false, false);
   }
 #undef BA_K1_LAUNCH
   BA_LAUNCH_CHECK();

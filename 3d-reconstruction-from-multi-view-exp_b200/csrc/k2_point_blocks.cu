@@ -188,6 +188,8 @@ k2b_point_solve_kernel(int64_t N, int M, int axis, const int64_t* __restrict__ o
   const double c = use_ctl ? ctl->c : c_host;
   const double damp = 1.0 + c;
   const int lane = threadIdx.x & 31;
+  extern __shared__ double k2b_stage[];
+  double* st = k2b_stage + (threadIdx.x >> 5) * 864;  // 32 observations x 27 doubles per warp
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t j = warp; j < N; j += nwarps) {
@@ -228,60 +230,81 @@ k2b_point_solve_kernel(int64_t N, int M, int axis, const int64_t* __restrict__ o
     }
     const int64_t lo = DENSE ? j * M : obs_ptr[j];
     const int64_t hi = DENSE ? lo + M : obs_ptr[j + 1];
-    for (int64_t o = lo + lane; o < hi; o += 32) {
-      const int i = DENSE ? (int)(o - lo) : obs_cam[o];
-      const uint32_t mask = gauge_mask(i, axis);
-      const double2* rp = reinterpret_cast<const double2*>(JP + (size_t)o * kJP);
-      const double2 p1 = rp[1], p2 = rp[2], p3 = rp[3];
-      const double a0 = p1.x, a1 = p1.y, a2 = p2.x, b0 = p2.y, b1 = p3.x, b2 = p3.y;
-      // T = 2 Jx L^-T  (2x3): T[k][d] = 2 sum_b Jx[k][b] m[d][b]
-      const double ta0 = 2.0 * (a0 * m00), ta1 = 2.0 * (a0 * m10 + a1 * m11),
-                   ta2 = 2.0 * (a0 * m20 + a1 * m21 + a2 * m22);
-      const double tb0 = 2.0 * (b0 * m00), tb1 = 2.0 * (b0 * m10 + b1 * m11),
-                   tb2 = 2.0 * (b0 * m20 + b1 * m21 + b2 * m22);
-      const double2* rc = reinterpret_cast<const double2*>(JC + (size_t)o * kJC);
-      double jc[kJC];
+    for (int64_t o0 = lo; o0 < hi; o0 += 32) {
+      const int64_t o = o0 + lane;
+      const int cnt = (int)(hi - o0 < 32 ? hi - o0 : 32);
+      if (o < hi) {
+        const int i = DENSE ? (int)(o - lo) : obs_cam[o];
+        const uint32_t mask = gauge_mask(i, axis);
+        const double2* rp = reinterpret_cast<const double2*>(JP + (size_t)o * kJP);
+        const double2 p1 = rp[1], p2 = rp[2], p3 = rp[3];
+        const double a0 = p1.x, a1 = p1.y, a2 = p2.x, b0 = p2.y, b1 = p3.x, b2 = p3.y;
+        // T = 2 Jx L^-T  (2x3): T[k][d] = 2 sum_b Jx[k][b] m[d][b]
+        const double ta0 = 2.0 * (a0 * m00), ta1 = 2.0 * (a0 * m10 + a1 * m11),
+                     ta2 = 2.0 * (a0 * m20 + a1 * m21 + a2 * m22);
+        const double tb0 = 2.0 * (b0 * m00), tb1 = 2.0 * (b0 * m10 + b1 * m11),
+                     tb2 = 2.0 * (b0 * m20 + b1 * m21 + b2 * m22);
+        const double2* rc = reinterpret_cast<const double2*>(JC + (size_t)o * kJC);
+        double jc[kJC];
 #pragma unroll
-      for (int k = 1; k < kJC / 2; ++k) {
-        const double2 t2 = rc[k];
-        jc[2 * k] = t2.x;
-        jc[2 * k + 1] = t2.y;
-      }
-      // Y[a][d] = Jc0[a] T[0][d] + Jc1[a] T[1][d]
+        for (int k = 1; k < kJC / 2; ++k) {
+          const double2 t2 = rc[k];
+          jc[2 * k] = t2.x;
+          jc[2 * k + 1] = t2.y;
+        }
+        // Y[a][d] = Jc0[a] T[0][d] + Jc1[a] T[1][d], staged in shared memory so that the warp
+        // writes whole contiguous runs (the per-lane 72-byte pieces would be partial sectors)
 #pragma unroll
-      for (int a = 0; a < 9; ++a) {
-        const bool pin = (mask >> a) & 1u;
-        const double ja = pin ? 0.0 : jc[2 + a], jb = pin ? 0.0 : jc[11 + a];
-        const double y0 = ja * ta0 + jb * tb0;
-        const double y1 = ja * ta1 + jb * tb1;
-        const double y2 = ja * ta2 + jb * tb2;
-        if (DENSE) {
-          const size_t col = 9 * (size_t)i + a;
-          Yt[(size_t)(3 * j + 0) * ld + col] = y0;
-          Yt[(size_t)(3 * j + 1) * ld + col] = y1;
-          Yt[(size_t)(3 * j + 2) * ld + col] = y2;
-        } else {
-          double* y = Ysp + (size_t)o * 27;
-          y[a] = y0;
-          y[9 + a] = y1;
-          y[18 + a] = y2;
+        for (int a = 0; a < 9; ++a) {
+          const bool pin = (mask >> a) & 1u;
+          const double ja = pin ? 0.0 : jc[2 + a], jb = pin ? 0.0 : jc[11 + a];
+          const double y0 = ja * ta0 + jb * tb0;
+          const double y1 = ja * ta1 + jb * tb1;
+          const double y2 = ja * ta2 + jb * tb2;
+          if (DENSE) {
+            st[9 * lane + a] = y0;
+            st[288 + 9 * lane + a] = y1;
+            st[576 + 9 * lane + a] = y2;
+          } else {
+            st[27 * lane + a] = y0;
+            st[27 * lane + 9 + a] = y1;
+            st[27 * lane + 18 + a] = y2;
+          }
         }
       }
+      __syncwarp();
+      if (DENSE) {
+        const size_t col0 = 9 * (size_t)(o0 - lo);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          double* dst = Yt + (size_t)(3 * j + d) * ld + col0;
+          for (int k = lane; k < 9 * cnt; k += 32) dst[k] = st[288 * d + k];
+        }
+      } else {
+        double* dst = Ysp + (size_t)o0 * 27;
+        for (int k = lane; k < 27 * cnt; k += 32) dst[k] = st[k];
+      }
+      __syncwarp();
     }
   }
 }
 
 int launch_k2b(ba_engine* e, bool conditional, double c_host, cudaStream_t s) {
   const int use_ctl = conditional ? 1 : 0;
+  constexpr size_t kStage = 8 * 864 * sizeof(double);
+  BA_CUDA(cudaFuncSetAttribute(k2b_point_solve_kernel<true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStage));
+  BA_CUDA(cudaFuncSetAttribute(k2b_point_solve_kernel<false>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStage));
   int64_t blocks = (e->N + 7) / 8;
   const int64_t cap = (int64_t)e->num_sms * 16;
   const int grid = (int)(blocks < cap ? blocks : cap);
   if (e->dense)
-    k2b_point_solve_kernel<true><<<grid, 256, 0, s>>>(
+    k2b_point_solve_kernel<true><<<grid, 256, kStage, s>>>(
         e->N, e->M, e->axis, e->obs_ptr, e->obs_cam, e->JP, e->JC, e->V, e->GPT, c_host, e->ctl,
         use_ctl, e->LINV, e->Z, e->Yt, e->n_pad, e->rhs_row, e->Ysp);
   else
-    k2b_point_solve_kernel<false><<<grid, 256, 0, s>>>(
+    k2b_point_solve_kernel<false><<<grid, 256, kStage, s>>>(
         e->N, e->M, e->axis, e->obs_ptr, e->obs_cam, e->JP, e->JC, e->V, e->GPT, c_host, e->ctl,
         use_ctl, e->LINV, e->Z, e->Yt, e->n_pad, e->rhs_row, e->Ysp);
   BA_LAUNCH_CHECK();

@@ -1,0 +1,313 @@
+// K4 (factor/solve part): blocked right-looking Cholesky of the reduced camera system and the
+// back substitution, replacing reference lib/bundle_adjustment.py:146 (`np.linalg.solve`, LAPACK
+// dgesv).  The system is symmetric positive definite, so LU with pivoting is not needed; the
+// survey measured <= 3e-14 relative effect on every per-iteration cost.
+//
+// Layout: S is n_pad x n_pad row-major (lower triangle used); row `rhs_row` = n carries the
+// right-hand side and is swept along as one more row, so after the factorisation it holds
+// y = L^-1 b.  Only L^T x = y is left for chol_backsolve_kernel.
+//
+// Per 64-column panel two launches:
+//   chol_panel_kernel   every block eliminates the tall panel [diagonal block; its 64 rows] in
+//                       shared memory (re-factoring the diagonal block per block is cheaper than
+//                       a third launch, and the rows below need no separate triangular solve).
+//                       Block 0 carries the rows of the identity instead, which yields
+//                       W = L_D^-T for the back substitution (no serial solve there either).
+//                       Writes L rows in place and a k-major copy Lt for the update.
+//   chol_update_kernel  trailing update S -= L_panel L_panel^T on 64x64 tiles.
+#include "ba_common.cuh"
+
+namespace ba {
+
+constexpr int NB = kCholNB;
+
+// Reciprocal to full double precision (<= ~1 ulp) with a short dependency chain: the hardware
+// seed (MUFU.RCP64H, ~2^-20) and two Newton steps.  FP64 latency dominates the pivot chain below.
+__device__ __forceinline__ double rcp_newton(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = fma(r, fma(-d, r, 1.0), r);
+  r = fma(r, fma(-d, r, 1.0), r);
+  return r;
+}
+
+constexpr int kPanelThreads = 2 * NB;  // one thread per row of the tall panel
+
+__global__ void __launch_bounds__(kPanelThreads)
+chol_panel_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb,
+                  double* __restrict__ Lt, double* __restrict__ W, ba_lm_state* ctl, int use_ctl) {
+  if (use_ctl && ctl->done) return;
+  extern __shared__ double psm[];
+  // tall panel T[128][65]: rows 0..63 the diagonal block, rows 64..127 this block's rows
+  double(*T)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(psm);
+  double* col = psm + 2 * NB * (NB + 1);  // [2][128] published pivot column (double buffered;
+                                          // entries 64..127 stay zero: shifted-out window columns)
+  double* piv = col + 4 * NB;             // [64] pivots d_k
+  __shared__ int s_fail;
+  const int tid = threadIdx.x;
+  // block 0 carries the rows of the identity (-> W = L_D^-T), block b >= 1 the 64 rows from rbase
+  const int rbase = k0 + nb + ((int)blockIdx.x - 1) * NB;
+  if (tid == 0) s_fail = 0;
+  for (int q = tid; q < 4 * NB; q += kPanelThreads) col[q] = 0.0;
+  {
+    // coalesced loads, all issued before the first use (L2 latency paid once)
+    double vd[32], va[32];
+    const int c = tid & 63;
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      const int r = (tid >> 6) + 2 * u;
+      vd[u] = (r == c) ? 1.0 : 0.0;
+      if (r < nb && c <= r) vd[u] = S[(size_t)(k0 + r) * ld + k0 + c];
+      va[u] = (blockIdx.x == 0 && r == c) ? 1.0 : 0.0;
+      if (blockIdx.x != 0 && rbase + r < n_rows && c < nb) va[u] = S[(size_t)(rbase + r) * ld + k0 + c];
+    }
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+      const int r = (tid >> 6) + 2 * u;
+      T[r][c] = vd[u];
+      T[NB + r][c] = va[u];
+    }
+  }
+  __syncthreads();
+  // Each thread keeps one row of the tall panel in registers.  Right-looking elimination with
+  // unscaled columns (A = Lu D^-1 Lu^T):  a[r][c] -= a[r][k] a[c][k] / d_k  for c > k (diagonal
+  // block: c <= r).  The rows below the diagonal block ride along, so there is no separate
+  // triangular solve.  Per column: the diagonal-block rows publish their column-k entry, one
+  // barrier, then every row does broadcast loads + FMAs from registers.  Columns are processed
+  // in groups of 8 with the register window shifted after each group, so the (unrolled) body is
+  // 8 columns long and stays in the instruction cache.
+  const int r = tid;         // row of the tall panel
+  const bool drow = r < NB;  // diagonal-block row
+  double a[NB];              // window: a[j] <-> column kb + j
+#pragma unroll
+  for (int c = 0; c < NB; ++c) a[c] = T[r][c];
+  for (int kb = 0; kb < NB; kb += 8) {
+    const int live = (NB - kb) >> 3;  // column groups of the window still inside the panel
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int k = kb + kk;
+      double* ck = col + (kk & 1) * (2 * NB);
+      if (drow && r >= k) ck[r] = a[kk];
+      __syncthreads();
+      const double d = ck[k];
+      if (r == k) piv[k] = d;
+      const double invd = rcp_newton(d);
+      const double la = a[kk] * invd;
+      // No per-element predicates: rows r <= k and the upper triangle of the diagonal block
+      // accumulate values nobody reads (only entries with column <= row are published/stored).
+      const double2* ck2 = reinterpret_cast<const double2*>(ck + kb);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (g < live) {  // block-uniform
+#pragma unroll
+          for (int jp = 0; jp < 4; ++jp) {
+            const int j = 8 * g + 2 * jp;
+            if (j + 1 > kk) {
+              const double2 cv = ck2[j >> 1];
+              if (j > kk) a[j] = fma(-la, cv.x, a[j]);
+              a[j + 1] = fma(-la, cv.y, a[j + 1]);
+            }
+          }
+        }
+      }
+    }
+    // the 8 finished (unscaled) columns go back to the tile; shift the window
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) T[r][kb + kk] = a[kk];
+#pragma unroll
+    for (int j = 0; j < NB - 8; ++j) a[j] = a[j + 8];
+#pragma unroll
+    for (int j = NB - 8; j < NB; ++j) a[j] = 0.0;
+  }
+  __syncthreads();
+  if (tid < NB) {
+    const double d = piv[tid];
+    if (tid < nb && !(d > 0.0)) s_fail = 1;
+    piv[tid] = rsqrt(d);  // = 1 / L[tid][tid]
+  }
+  __syncthreads();
+  for (int q = tid; q < 2 * NB * NB; q += kPanelThreads)  // L[r][c] = Lu[r][c] / sqrt(d_c)
+    T[q >> 6][q & 63] *= piv[q & 63];
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    if (tid == 0 && s_fail) ctl->chol_fail = 1;
+    // L_D (k-major) for the trailing update: Lt[m][k0 + r] = L_D[r][m]
+    for (int q = tid; q < NB * NB; q += kPanelThreads) {
+      const int m = q >> 6, rr = q & 63;
+      if (m < nb && rr < nb) Lt[(size_t)m * ld + k0 + rr] = rr >= m ? T[rr][m] : 0.0;
+    }
+    // W = L_D^-T from the identity rows
+    for (int q = tid; q < NB * NB; q += kPanelThreads) W[q] = T[NB + (q >> 6)][q & 63];
+  } else {
+    for (int q = tid; q < NB * NB; q += kPanelThreads) {
+      const int rr = q >> 6, c = q & 63;
+      if (rbase + rr < n_rows && c < nb) S[(size_t)(rbase + rr) * ld + k0 + c] = T[NB + rr][c];
+    }
+    for (int q = tid; q < NB * NB; q += kPanelThreads) {
+      const int c = q >> 6, rr = q & 63;
+      if (rbase + rr < n_rows && c < nb) Lt[(size_t)c * ld + rbase + rr] = T[NB + rr][c];
+    }
+  }
+}
+
+// Trailing update S[r][c] -= sum_m L[r][k0+m] L[c][k0+m] on 64x64 tiles of the lower triangle
+// (rows/cols >= k0+nb, rows < n_rows).  The diagonal blocks of S keep their pre-factor content:
+// nothing reads L_D from S afterwards (the back substitution uses W = L_D^-T).
+__global__ void __launch_bounds__(256)
+chol_update_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb,
+                   const double* __restrict__ Lt, const ba_lm_state* ctl, int use_ctl) {
+  if (use_ctl && ctl->done) return;
+  const int tid = threadIdx.x;
+  const int t0 = k0 + nb;
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (tj > ti) return;
+  const int r0 = t0 + ti * 64, c0 = t0 + tj * 64;
+  if (r0 >= n_rows) return;
+  constexpr int MH = NB;  // the whole panel depth in one pass: all loads in flight at once
+  extern __shared__ double usm[];
+  double(*sA)[64 + 1] = reinterpret_cast<double(*)[64 + 1]>(usm);
+  double(*sB)[64 + 1] = reinterpret_cast<double(*)[64 + 1]>(usm + MH * 65);
+  const int ty = tid / 16, tx = tid % 16;  // thread owns rows ty+16*i, cols tx+16*j
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int m0 = 0; m0 < nb; m0 += MH) {
+    __syncthreads();
+    {
+      double va[16], vb[16];
+      const int x = tid & 63;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int m = m0 + (tid >> 6) + 4 * u;
+        va[u] = (m < nb && r0 + x < n_rows) ? Lt[(size_t)m * ld + r0 + x] : 0.0;
+        vb[u] = (m < nb && c0 + x < n_rows) ? Lt[(size_t)m * ld + c0 + x] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        sA[(tid >> 6) + 4 * u][x] = va[u];
+        sB[(tid >> 6) + 4 * u][x] = vb[u];
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int m = 0; m < MH; ++m) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sA[m][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = sB[m][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = r0 + ty + 16 * i, c = c0 + tx + 16 * j;
+      if (r < n_rows && c <= r) S[(size_t)r * ld + c] -= acc[i][j];
+    }
+}
+
+// Back substitution L^T x = y (y = row rhs_row of the factor) by 64-column blocks from the
+// last one: rhs_B = y_B - L[below, B]^T x_below (GEMV), x_B = W_B rhs_B with W_B = L_BB^-T from
+// the panel kernel.  One block; x lives in shared memory.
+__global__ void __launch_bounds__(1024)
+chol_backsolve_kernel(const double* __restrict__ S, int ld, int n, int rhs_row,
+                      const double* __restrict__ W, double* __restrict__ dxi,
+                      const ba_lm_state* ctl, int use_ctl) {
+  if (use_ctl && ctl->done) return;
+  extern __shared__ double sm[];
+  double* x = sm;             // [n]
+  double* red = sm + n;       // [16][64]
+  double* rhs = red + 16 * 64;  // [64]
+  const int tid = threadIdx.x;
+  const int tx = tid & 63, ty = tid >> 6;  // 64 columns x 16 row groups
+  const int nblk = (n + 63) / 64;
+  for (int blk = nblk - 1; blk >= 0; --blk) {
+    const int b0 = blk * 64;
+    const int b1 = b0 + 64 < n ? b0 + 64 : n;
+    const int w = b1 - b0;
+    // W row for the second product and y_B are fetched now so their L2 latency overlaps the GEMV
+    const int wj = tid >> 4, wpart = tid & 15;
+    const double* Wj = W + (size_t)blk * NB * NB + (size_t)wj * NB;
+    double wv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wv[i] = Wj[wpart + 16 * i];
+    const double yb = (ty == 0 && tx < w) ? S[(size_t)rhs_row * ld + b0 + tx] : 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // independent chains: FP64 latency is long
+    if (tx < w) {
+      int k = b1 + ty;
+      for (; k + 48 < n; k += 64) {
+        const double s0 = S[(size_t)k * ld + b0 + tx], s1 = S[(size_t)(k + 16) * ld + b0 + tx];
+        const double s2 = S[(size_t)(k + 32) * ld + b0 + tx], s3 = S[(size_t)(k + 48) * ld + b0 + tx];
+        a0 = fma(s0, x[k], a0);
+        a1 = fma(s1, x[k + 16], a1);
+        a2 = fma(s2, x[k + 32], a2);
+        a3 = fma(s3, x[k + 48], a3);
+      }
+      for (; k < n; k += 16) a0 = fma(S[(size_t)k * ld + b0 + tx], x[k], a0);
+    }
+    red[ty * 64 + tx] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ty == 0) {
+      double p[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int g = 0; g < 16; ++g) p[g & 3] += red[g * 64 + tx];
+      rhs[tx] = yb - ((p[0] + p[1]) + (p[2] + p[3]));
+    }
+    __syncthreads();
+    {
+      // x_B[j] = sum_c W[j][c] rhs[c]; thread (j = tid / 16, part = tid % 16)
+      const int j = wj, part = wpart;
+      double s = (wv[0] * rhs[part] + wv[1] * rhs[part + 16]) +
+                 (wv[2] * rhs[part + 32] + wv[3] * rhs[part + 48]);
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (part == 0 && j < w) x[b0 + j] = s;
+    }
+    __syncthreads();
+  }
+  for (int k = tid; k < n; k += 1024) dxi[k] = x[k];
+}
+
+int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
+  const int use_ctl = conditional ? 1 : 0;
+  constexpr size_t kPanelSmem = (2 * NB * (NB + 1) + 5 * NB) * sizeof(double);
+  BA_CUDA(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)kPanelSmem));
+  constexpr size_t kUpdateSmem = 2 * NB * 65 * sizeof(double);
+  BA_CUDA(cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)kUpdateSmem));
+  const int n = e->n_full, n_rows = e->rhs_row + 1, ld = e->n_pad;
+  int panel = 0;
+  for (int k0 = 0; k0 < n; k0 += NB, ++panel) {
+    const int nb = n - k0 < NB ? n - k0 : NB;
+    const int below = n_rows - (k0 + nb);
+    const int pblocks = 1 + (below + NB - 1) / NB;
+    chol_panel_kernel<<<pblocks, kPanelThreads, kPanelSmem, s>>>(e->P(), ld, n_rows, k0, nb, e->Lt,
+                                              e->Winv + (size_t)panel * NB * NB, e->ctl, use_ctl);
+    BA_LAUNCH_CHECK();
+    const int nt = below > 0 ? (below + 63) / 64 : 1;
+    dim3 grid(nt, nt);
+    chol_update_kernel<<<grid, 256, kUpdateSmem, s>>>(e->P(), ld, n_rows, k0, nb, e->Lt, e->ctl, use_ctl);
+    BA_LAUNCH_CHECK();
+  }
+  const size_t smem = ((size_t)n + 16 * 64 + 64) * sizeof(double);
+  if (smem > 220 * 1024) {
+    set_error("reduced system too large for the single-block back substitution (n=%d)", n);
+    return BA_ERR_INVALID;
+  }
+  BA_CUDA(cudaFuncSetAttribute(chol_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  chol_backsolve_kernel<<<1, 1024, smem, s>>>(e->P(), ld, n, e->rhs_row, e->Winv, e->dxi, e->ctl,
+                                              use_ctl);
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}
+
+}  // namespace ba

@@ -56,210 +56,6 @@ int launch_assemble(ba_engine* e, bool conditional, double c_host, cudaStream_t 
   return BA_OK;
 }
 
-// ---- blocked Cholesky -------------------------------------------------------------------------
-constexpr int NB = kCholNB;
-
-// Panel step at column k0 (nb <= NB columns): every block factors the nb x nb diagonal block in
-// shared memory (redundantly: cheaper than another launch), then solves its 256 rows below the
-// block against L_D^T, one row per thread held in registers.  Outputs: S rows below (in place)
-// and the k-major copy Lt[m][r] = L[r][k0+m] for the trailing update.  Block 0 also emits L_D
-// into Lt; the update launch copies it into S (other blocks may still be reading D from S).
-__global__ void __launch_bounds__(256)
-chol_panel_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb,
-                  double* __restrict__ Lt, ba_lm_state* ctl, int use_ctl) {
-  if (use_ctl && ctl->done) return;
-  __shared__ double sD[NB][NB + 1];
-  __shared__ int s_fail;
-  const int tid = threadIdx.x;
-  if (tid == 0) s_fail = 0;
-  for (int q = tid; q < NB * NB; q += 256) {
-    const int r = q / NB, c = q % NB;
-    double v = (r == c) ? 1.0 : 0.0;
-    if (r < nb && c <= r) v = S[(size_t)(k0 + r) * ld + k0 + c];
-    sD[r][c] = v;
-  }
-  __syncthreads();
-  for (int k = 0; k < nb; ++k) {
-    if (tid == 0) {
-      const double d = sD[k][k];
-      if (!(d > 0.0)) s_fail = 1;
-      sD[k][k] = sqrt(d);
-    }
-    __syncthreads();
-    const double dk = sD[k][k];
-    for (int r = k + 1 + tid; r < nb; r += 256) sD[r][k] /= dk;
-    __syncthreads();
-    const int w = nb - k - 1;
-    for (int q = tid; q < w * w; q += 256) {
-      const int r = k + 1 + q / w, c = k + 1 + q % w;
-      if (c <= r) sD[r][c] -= sD[r][k] * sD[c][k];
-    }
-    __syncthreads();
-  }
-  if (blockIdx.x == 0) {
-    if (tid == 0 && s_fail) ctl->chol_fail = 1;
-    for (int q = tid; q < nb * nb; q += 256) {
-      const int m = q / nb, r = q % nb;  // Lt[m][k0 + r] = L_D[r][m]
-      Lt[(size_t)m * ld + k0 + r] = r >= m ? sD[r][m] : 0.0;
-    }
-  }
-  // triangular solve for the rows below: x L_D^T = a
-  const int r = k0 + nb + blockIdx.x * 256 + tid;
-  if (r >= n_rows) return;
-  double x[NB];
-  double* row = S + (size_t)r * ld + k0;
-#pragma unroll
-  for (int c = 0; c < NB; ++c) x[c] = c < nb ? row[c] : 0.0;
-#pragma unroll
-  for (int c = 0; c < NB; ++c) {
-    const double xc = x[c] / sD[c][c];
-    x[c] = xc;
-#pragma unroll
-    for (int c2 = c + 1; c2 < NB; ++c2) x[c2] -= xc * sD[c2][c];
-  }
-#pragma unroll
-  for (int c = 0; c < NB; ++c)
-    if (c < nb) {
-      row[c] = x[c];
-      Lt[(size_t)c * ld + r] = x[c];
-    }
-}
-
-// Trailing update S[r][c] -= sum_m L[r][k0+m] L[c][k0+m] on 64x64 tiles of the lower triangle
-// (rows/cols >= k0+nb, rows < n_rows); block (0,0) also copies L_D from Lt into S.
-__global__ void __launch_bounds__(256)
-chol_update_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb,
-                   const double* __restrict__ Lt, const ba_lm_state* ctl, int use_ctl) {
-  if (use_ctl && ctl->done) return;
-  const int tid = threadIdx.x;
-  if (blockIdx.x == 0 && blockIdx.y == 0)
-    for (int q = tid; q < nb * nb; q += 256) {
-      const int r = q / nb, m = q % nb;
-      if (m <= r) S[(size_t)(k0 + r) * ld + k0 + m] = Lt[(size_t)m * ld + k0 + r];
-    }
-  const int t0 = k0 + nb;
-  const int ti = blockIdx.y, tj = blockIdx.x;
-  if (tj > ti) return;
-  const int r0 = t0 + ti * 64, c0 = t0 + tj * 64;
-  if (r0 >= n_rows) return;
-  constexpr int MH = 32;  // k rows staged per pass (static shared memory <= 48 KB)
-  __shared__ double sA[MH][64 + 1];
-  __shared__ double sB[MH][64 + 1];
-  const int ty = tid / 16, tx = tid % 16;  // thread owns rows ty+16*i, cols tx+16*j
-  double acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int m0 = 0; m0 < nb; m0 += MH) {
-    __syncthreads();
-    for (int q = tid; q < MH * 64; q += 256) {
-      const int m = m0 + q / 64, x = q % 64;
-      sA[q / 64][x] = (m < nb && r0 + x < n_rows) ? Lt[(size_t)m * ld + r0 + x] : 0.0;
-      sB[q / 64][x] = (m < nb && c0 + x < n_rows) ? Lt[(size_t)m * ld + c0 + x] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int m = 0; m < MH; ++m) {
-      double a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = sA[m][ty + 16 * i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = sB[m][tx + 16 * j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = r0 + ty + 16 * i, c = c0 + tx + 16 * j;
-      if (r < n_rows && c <= r) S[(size_t)r * ld + c] -= acc[i][j];
-    }
-}
-
-// Back substitution L^T x = y with y = row rhs_row of the factor; one block, x in shared memory.
-__global__ void __launch_bounds__(1024)
-chol_backsolve_kernel(const double* __restrict__ S, int ld, int n, int rhs_row,
-                      double* __restrict__ dxi, const ba_lm_state* ctl, int use_ctl) {
-  if (use_ctl && ctl->done) return;
-  extern __shared__ double sm[];
-  double* x = sm;                       // [n]
-  double* sD = sm + n;                  // [64][65]
-  double* red = sD + 64 * 65;           // [16][64]
-  const int tid = threadIdx.x;
-  const int tx = tid & 63, ty = tid >> 6;  // 64 columns x 16 row groups
-  const int nblk = (n + 63) / 64;
-  for (int blk = nblk - 1; blk >= 0; --blk) {
-    const int b0 = blk * 64;
-    const int b1 = b0 + 64 < n ? b0 + 64 : n;
-    const int w = b1 - b0;
-    // acc_c = sum_{k >= b1} L[k][c] x[k]
-    double acc = 0.0;
-    if (tx < w)
-      for (int k = b1 + ty; k < n; k += 16) acc += S[(size_t)k * ld + b0 + tx] * x[k];
-    red[ty * 64 + tx] = acc;
-    for (int q = tid; q < 64 * 64; q += 1024) {
-      const int r = q >> 6, c = q & 63;
-      sD[r * 65 + c] = (r < w && c <= r) ? S[(size_t)(b0 + r) * ld + b0 + c] : (r == c ? 1.0 : 0.0);
-    }
-    __syncthreads();
-    if (ty == 0) {
-      double s = 0.0;
-#pragma unroll
-      for (int g = 0; g < 16; ++g) s += red[g * 64 + tx];
-      red[tx] = (tx < w ? S[(size_t)rhs_row * ld + b0 + tx] : 0.0) - s;
-    }
-    __syncthreads();
-    if (tid < 32) {
-      // two columns per lane (tid, tid+32); solve from the last column up
-      double v0 = red[tid], v1 = red[tid + 32];
-      for (int c = 63; c >= 0; --c) {
-        const double vc = __shfl_sync(0xffffffffu, c < 32 ? v0 : v1, c & 31);
-        const double xc = vc / sD[c * 65 + c];
-        if (c == tid) v0 = xc;
-        if (c == tid + 32) v1 = xc;
-        // eliminate x_c from the columns above: acc_k -= L[c][k] x_c for k < c
-        if (tid < c) v0 -= sD[c * 65 + tid] * xc;
-        if (tid + 32 < c) v1 -= sD[c * 65 + tid + 32] * xc;
-      }
-      if (tid < w) x[b0 + tid] = v0;
-      if (tid + 32 < w) x[b0 + tid + 32] = v1;
-    }
-    __syncthreads();
-  }
-  for (int k = tid; k < n; k += 1024) dxi[k] = x[k];
-}
-
-int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
-  const int use_ctl = conditional ? 1 : 0;
-  const int n = e->n_full, n_rows = e->rhs_row + 1, ld = e->n_pad;
-  for (int k0 = 0; k0 < n; k0 += NB) {
-    const int nb = n - k0 < NB ? n - k0 : NB;
-    const int below = n_rows - (k0 + nb);
-    const int pblocks = below > 0 ? (below + 255) / 256 : 1;
-    chol_panel_kernel<<<pblocks, 256, 0, s>>>(e->P(), ld, n_rows, k0, nb, e->Lt, e->ctl, use_ctl);
-    BA_LAUNCH_CHECK();
-    const int nt = below > 0 ? (below + 63) / 64 : 1;
-    dim3 grid(nt, nt);
-    chol_update_kernel<<<grid, 256, 0, s>>>(e->P(), ld, n_rows, k0, nb, e->Lt, e->ctl, use_ctl);
-    BA_LAUNCH_CHECK();
-  }
-  const size_t smem = ((size_t)n + 64 * 65 + 16 * 64) * sizeof(double);
-  if (smem > 220 * 1024) {
-    set_error("reduced system too large for the single-block back substitution (n=%d)", n);
-    return BA_ERR_INVALID;
-  }
-  BA_CUDA(cudaFuncSetAttribute(chol_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem));
-  chol_backsolve_kernel<<<1, 1024, smem, s>>>(e->P(), ld, n, e->rhs_row, e->dxi, e->ctl, use_ctl);
-  BA_LAUNCH_CHECK();
-  return BA_OK;
-}
-
 // ---- camera update (:263-281, lib/utils.py:10-29) -----------------------------------------------
 __global__ void camera_update_kernel(int M, double f0, const double* __restrict__ dxi,
                                      const double* __restrict__ f, const double* __restrict__ u,
