@@ -1,0 +1,84 @@
+"""Sharded CUDA path on ONE GPU: two ranks (processes) share cuda:0, each owns half of the
+points, and the two all-reduces per inner solve go through gloo (NCCL needs one GPU per rank;
+the multi-GPU NCCL run is exercised by `bench.py --gpus N`).  Checks the engine's phase API
+(`ba_lm_phase_*`, reduce / cost buffers) against the reference's golden trajectory."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, case, out_dir):
+    import contextlib
+    import io
+
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import ba_b200
+        from conftest import case_inputs, load_golden
+
+        sharded = ba_b200.submodule("sharded")
+        adjuster = ba_b200.submodule("bundle_adjuster")
+        g = load_golden(case)
+        x, vis, X0, K0, R0, t0, axis, f0 = case_inputs(g)
+        full = adjuster.ObservationList.from_dense(x, vis)
+        lo, hi = sharded.shard_bounds(full.n_points, world, full.obs_ptr)[rank]
+        a, b = int(full.obs_ptr[lo]), int(full.obs_ptr[hi])
+        adj = ba_b200.BundleAdjuster.from_observations(
+            full.obs_ptr[lo:hi + 1] - full.obs_ptr[lo],
+            None if full.dense else full.obs_cam[a:b], full.obs_xy[a:b],
+            X0[lo:hi], K0, R0, t0, f0=f0, axis=axis, dense=full.dense, device=0,
+            process_group=dist.group.WORLD)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            X, K, R, t = adj.optimize(2.0, 1e-8, max_iter=100, is_debug=(rank == 0))
+        E = np.array([adj.records[0]["E_prev"]] + [r["E"] for r in adj.records])
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), E=E, X=X, K=K, R=R, t=t, lo=lo, hi=hi,
+                 lines=len(buf.getvalue().strip().splitlines()),
+                 nlog=len(adj.get_log()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("case", ["small_sparse_xup", "mid_dense_xup"])
+def test_two_ranks_on_one_gpu_match_reference(tmp_path, case):
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import load_golden
+
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), case, str(tmp_path)), nprocs=world, join=True)
+    g = load_golden(case)
+    out = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
+    X = np.zeros_like(g["X"])
+    for o in out:
+        assert o["E"].shape == g["E"].shape
+        np.testing.assert_allclose(o["E"], g["E"], rtol=1e-9)
+        np.testing.assert_allclose(o["K"], g["K"], atol=1e-6)
+        np.testing.assert_allclose(o["R"], g["R"], atol=1e-6)
+        np.testing.assert_allclose(o["t"], g["t"], atol=1e-6)
+        X[int(o["lo"]):int(o["hi"])] = o["X"]
+    np.testing.assert_allclose(X, g["X"], atol=1e-6)
+    # only rank 0 prints the reference's iteration lines; its debug log has one entry per state
+    assert int(out[0]["lines"]) == len(g["E"]) - 1 and int(out[1]["lines"]) == 0
+    assert int(out[0]["nlog"]) == len(g["E"])
