@@ -27,7 +27,22 @@ template <typename T>
 static int dev_alloc(T** p, size_t n) {
   *p = nullptr;
   if (n == 0) n = 1;
-  BA_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  // stream-ordered allocation from the device's default pool; the pool keeps freed memory
+  // (release threshold raised in create_engine), so engines created one after the other -- the
+  // usual way the reference's class is used -- do not pay cudaMalloc/cudaFree again
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(p), n * sizeof(T), (cudaStream_t)0));
+  return BA_OK;
+}
+
+static void dev_free(void* p) {
+  if (p) cudaFreeAsync(p, (cudaStream_t)0);
+}
+
+static int retain_pool_memory(int device) {
+  cudaMemPool_t pool;
+  BA_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t keep = UINT64_MAX;
+  BA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   return BA_OK;
 }
 
@@ -93,15 +108,15 @@ int build_camera_major_index(ba_engine* e, cudaStream_t s) {
   BA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, e->obs_cam, keys_out, vals_in,
                                           e->cm_perm, (int)n, 0, bits, s));
   void* tmp = nullptr;
-  BA_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+  BA_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, (cudaStream_t)0));
   BA_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, e->obs_cam, keys_out, vals_in, e->cm_perm,
                                           (int)n, 0, bits, s));
   cam_ptr_kernel<<<(e->M + 1 + 127) / 128, 128, 0, s>>>(e->M, n, keys_out, e->cam_ptr);
   BA_LAUNCH_CHECK();
   BA_CUDA(cudaStreamSynchronize(s));
-  cudaFree(tmp);
-  cudaFree(keys_out);
-  cudaFree(vals_in);
+  dev_free(tmp);
+  dev_free(keys_out);
+  dev_free(vals_in);
   return BA_OK;
 }
 
@@ -113,7 +128,7 @@ static void free_engine(ba_engine* e) {
                   e->GPT, e->Upart, e->Uloc, e->LINV, e->Z, e->Yt, e->Ysp, e->red, e->Spart, e->Lt, e->Winv,
                   e->dxi, e->cost_part, e->cost_buf, e->ctl, e->rec};
   for (void* p : ptrs)
-    if (p) cudaFree(p);
+    dev_free(p);
   if (e->ctl_host) cudaFreeHost(e->ctl_host);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -154,6 +169,7 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
     return BA_ERR_INVALID;
   }
   BA_CUDA(cudaSetDevice(p->device));
+  BA_TRY(retain_pool_memory(p->device));
   ba_engine* e = new (std::nothrow) ba_engine();
   if (!e) { set_error("out of host memory"); return BA_ERR_CUDA; }
   e->prob = *p;

@@ -290,7 +290,7 @@ int syrk_choose_splits(int n_pad, int tile, int64_t k_pad, int num_sms) {
   const int64_t min_chunks = 768 / syrk_kc(tile);
   int64_t s_max = n_chunks / min_chunks;
   if (s_max < 1) s_max = 1;
-  int64_t s_cap = (int64_t)12 * slots / n_tiles;
+  int64_t s_cap = (int64_t)24 * slots / n_tiles;
   if (s_cap < 1) s_cap = 1;
   const int s_hi = (int)(s_max < s_cap ? s_max : s_cap);
   int best = s_hi;
@@ -339,7 +339,7 @@ int launch_k3(ba_engine* e, bool conditional, cudaStream_t s) {
     BA_LAUNCH_CHECK();
   }
   if (e->dense) {
-    if (e->syrk_tile == 128) return launch_syrk<128, 2, 4, 32>(e, ctl, s);
+    if (e->syrk_tile == 128) return launch_syrk<128, 4, 4, 32>(e, ctl, s);
     return launch_syrk<64, 2, 2, 16>(e, ctl, s);
   }
   const int64_t np = (int64_t)e->n_pad * e->n_pad;

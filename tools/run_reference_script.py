@@ -1,0 +1,38 @@
+"""Run one of the reference's own scripts UNCHANGED on the B200 engine.
+
+    python tools/run_reference_script.py /path/to/reference/euclidiean_reconstruction.py
+
+Puts this repo's package directory (which contains lib/bundle_adjustment.py) before the
+reference checkout on sys.path, so `from lib.bundle_adjustment import BundleAdjuster` resolves
+to the CUDA engine while every other `lib.*` module is the reference's.  If matplotlib is not
+installed a no-op stub is injected (the scripts only plot with it).
+"""
+import os
+import runpy
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+script = os.path.abspath(sys.argv[1])
+sys.path[:0] = [os.path.join(ROOT, "3d-reconstruction-from-multi-view-exp_b200"), os.path.dirname(script)]
+
+try:
+    import matplotlib  # noqa: F401
+except ImportError:
+    class _Anything:
+        def __getattr__(self, name):
+            return _Anything()
+
+        def __call__(self, *a, **k):
+            return _Anything()
+
+        def __iter__(self):
+            return iter(())
+
+    mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+    plt.__getattr__ = lambda name: _Anything()
+    plt.fignum_exists = lambda *_: False
+    mpl.pyplot = plt
+    sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
+
+runpy.run_path(script, run_name="__main__")
