@@ -89,6 +89,8 @@ struct ba_engine {
   double* obs_xy = nullptr;
   int64_t* cam_ptr = nullptr;  // [M+1] (sparse)
   int32_t* cm_perm = nullptr;  // [nobs] observation ids sorted by camera (sparse)
+  uint32_t* grp_bits = nullptr;  // [N][ceil(M/32)] visible cameras of a point per 32-camera group (sparse)
+  uint16_t* grp_pre = nullptr;   // [N][ceil(M/32)] observations of the point in lower groups (sparse)
   int64_t max_pt_obs = 0;
   bool have_obs = false, have_state = false;
 
@@ -215,6 +217,8 @@ int launch_decide(ba_engine* e, cudaStream_t s);
 int launch_lm_begin(ba_engine* e, double scale, double tol, int max_iter, int max_retries,
                     cudaStream_t s);
 int build_camera_major_index(ba_engine* e, cudaStream_t s);
+int build_group_index(ba_engine* e, cudaStream_t s);
+int launch_schur_sparse(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s);
 int fp64_peak(int device, int use_dmma, double* tflops);
 
 }  // namespace ba

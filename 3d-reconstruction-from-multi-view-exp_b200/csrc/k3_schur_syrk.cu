@@ -17,8 +17,7 @@
 //
 // Compute roofline (FP64 tensor): algorithmic flops = 3N * n (n + 1), n = 9M - 7.
 //
-// Sparse visibility: per-point outer products of the visible 9x3 blocks, scattered into P
-// with FP64 reductions (first correct version; DESIGN.md has the planned output-stationary form).
+// Sparse visibility: see k3_schur_sparse.cu (output-stationary, no atomics).
 #include "ba_common.cuh"
 
 namespace ba {
@@ -225,57 +224,6 @@ __global__ void stage_camera_blocks_kernel(int n, const double* __restrict__ src
   if (k < n) dst[k] = src[k];
 }
 
-// ---- sparse visibility ---------------------------------------------------------------------
-__global__ void zero_kernel(double* __restrict__ p, int64_t n, const ba_lm_state* ctl) {
-  if (ctl && ctl->done) return;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) p[k] = 0.0;
-}
-
-__global__ void __launch_bounds__(128)
-schur_sparse_atomic_kernel(int64_t N, const int64_t* __restrict__ obs_ptr,
-                           const int32_t* __restrict__ obs_cam, const double* __restrict__ Ysp,
-                           const double* __restrict__ Z, double* __restrict__ P, int ld,
-                           int rhs_row, const ba_lm_state* ctl) {
-  if (ctl && ctl->done) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t j = warp; j < N; j += nwarps) {
-    const int64_t lo = obs_ptr[j], hi = obs_ptr[j + 1];
-    const int m = (int)(hi - lo);
-    const double z0 = Z[3 * j], z1 = Z[3 * j + 1], z2 = Z[3 * j + 2];
-    for (int a = 0; a < m; ++a) {
-      const int ia = obs_cam[lo + a];
-      double ya[27];
-      const double* Ya = Ysp + (size_t)(lo + a) * 27;
-#pragma unroll
-      for (int k = 0; k < 27; ++k) ya[k] = Ya[k];
-      if (lane < 9) {
-        double v = 0.0;
-#pragma unroll
-        for (int k = 0; k < 9; ++k)
-          if (k == lane) v = z0 * ya[k] + z1 * ya[9 + k] + z2 * ya[18 + k];
-        atomicAdd(P + (size_t)rhs_row * ld + 9 * ia + lane, v);
-      }
-      for (int b = lane; b <= a; b += 32) {
-        const int ib = obs_cam[lo + b];
-        double yb[27];
-        const double* Yb = Ysp + (size_t)(lo + b) * 27;
-#pragma unroll
-        for (int k = 0; k < 27; ++k) yb[k] = Yb[k];
-        double* dst = P + (size_t)(9 * ia) * ld + 9 * ib;  // ia >= ib: lower triangle
-#pragma unroll
-        for (int r = 0; r < 9; ++r)
-#pragma unroll
-          for (int s = 0; s < 9; ++s)
-            atomicAdd(dst + (size_t)r * ld + s,
-                      ya[r] * yb[s] + ya[9 + r] * yb[9 + s] + ya[18 + r] * yb[18 + s]);
-      }
-    }
-  }
-}
-
 // ---- host side --------------------------------------------------------------------------------
 static inline int syrk_kc(int tile) { return tile == 128 ? 32 : 16; }
 static inline int syrk_occupancy(int tile) { return tile == 128 ? 1 : 4; }
@@ -342,15 +290,7 @@ int launch_k3(ba_engine* e, bool conditional, cudaStream_t s) {
     if (e->syrk_tile == 128) return launch_syrk<128, 4, 4, 32>(e, ctl, s);
     return launch_syrk<64, 2, 2, 16>(e, ctl, s);
   }
-  const int64_t np = (int64_t)e->n_pad * e->n_pad;
-  zero_kernel<<<e->num_sms * 8, 256, 0, s>>>(e->P(), np, ctl);
-  BA_LAUNCH_CHECK();
-  int64_t blocks = (e->N + 3) / 4;
-  const int64_t cap = (int64_t)e->num_sms * 16;
-  schur_sparse_atomic_kernel<<<(int)(blocks < cap ? blocks : cap), 128, 0, s>>>(
-      e->N, e->obs_ptr, e->obs_cam, e->Ysp, e->Z, e->P(), e->n_pad, e->rhs_row, ctl);
-  BA_LAUNCH_CHECK();
-  return BA_OK;
+  return launch_schur_sparse(e, ctl, s);
 }
 
 }  // namespace ba
