@@ -40,6 +40,8 @@ constexpr int kCamTab = 16;   // doubles per camera in the derived table (128 B 
 constexpr int kJP = 8;        // doubles per observation, point-side row: e(2), de/dX (2x3)
 constexpr int kJC = 20;       // doubles per observation, camera-side row: e(2), de/dcam (2x9)
 constexpr int kUPart = 54;    // 45 unique entries of U_i + 9 of dF_i
+constexpr int kYcm = 24;      // doubles per observation in the camera-major factor array (sparse):
+                              // Jc row 0 (9), Jc row 1 (9), T = 2 Jx L^-T rows 0 and 1 (3 + 3)
 constexpr int kCholNB = 64;   // panel width of the blocked Cholesky
 constexpr int kMaxRecords = 4096;
 
@@ -89,9 +91,9 @@ struct ba_engine {
   double* obs_xy = nullptr;
   int64_t* cam_ptr = nullptr;  // [M+1] (sparse)
   int32_t* cm_perm = nullptr;  // [nobs] observation ids sorted by camera (sparse)
-  uint32_t* grp_bits = nullptr;  // [N][ceil(M/32)] visible cameras of a point per 32-camera group (sparse)
-  uint16_t* grp_pre = nullptr;   // [N][ceil(M/32)] observations of the point in lower groups (sparse)
-  int64_t max_pt_obs = 0;
+  int32_t* cm_pos = nullptr;   // [nobs] inverse of cm_perm: position of an observation in its camera's slice order (sparse)
+  uint2* bitpre = nullptr;     // [M][Wp] per camera: .x = bitmap word over points, .y = set bits in earlier words (sparse)
+  int64_t Wp = 0;              // words per camera bitmap, padded to a multiple of 32
   bool have_obs = false, have_state = false;
 
   // state: [0] current, [1] trial
@@ -109,6 +111,7 @@ struct ba_engine {
   double *LINV = nullptr, *Z = nullptr;
   double* Yt = nullptr;   // dense: [k_pad][n_pad]
   double* Ysp = nullptr;  // sparse: [nobs][27]
+  double* Ycm = nullptr;  // sparse: [nobs][kYcm] camera-major factors of Y (operand of the pair kernel)
   double* red = nullptr;  // [n_pad*n_pad | M*81 | M*9]
   int64_t red_len = 0;
   double* Spart = nullptr;  // split-K partial tiles
@@ -217,7 +220,7 @@ int launch_decide(ba_engine* e, cudaStream_t s);
 int launch_lm_begin(ba_engine* e, double scale, double tol, int max_iter, int max_retries,
                     cudaStream_t s);
 int build_camera_major_index(ba_engine* e, cudaStream_t s);
-int build_group_index(ba_engine* e, cudaStream_t s);
+int build_pair_index(ba_engine* e, cudaStream_t s);
 int launch_schur_sparse(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s);
 int fp64_peak(int device, int use_dmma, double* tflops);
 

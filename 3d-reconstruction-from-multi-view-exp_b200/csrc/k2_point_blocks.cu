@@ -177,13 +177,14 @@ int launch_camera_blocks(ba_engine* e, cudaStream_t s, bool conditional) {
 // One warp per point.  Dense layout of Y: Yt[(3j+d) * ld + 9i + a] (k-major operand of the
 // SYRK) with z_j in column rhs_col; sparse layout: Ysp[o][d][a].
 template <bool DENSE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k2b_point_solve_kernel(int64_t N, int M, int axis, const int64_t* __restrict__ obs_ptr,
                        const int32_t* __restrict__ obs_cam, const double* __restrict__ JP,
                        const double* __restrict__ JC, const double* __restrict__ V,
                        const double* __restrict__ GPT, double c_host, ba_lm_state* ctl,
                        int use_ctl, double* __restrict__ LINV, double* __restrict__ Z,
-                       double* __restrict__ Yt, int ld, int rhs_col, double* __restrict__ Ysp) {
+                       double* __restrict__ Yt, int ld, int rhs_col, double* __restrict__ Ysp,
+                       const int32_t* __restrict__ cm_pos, double* __restrict__ Ycm) {
   if (use_ctl && ctl->done) return;
   const double c = use_ctl ? ctl->c : c_host;
   const double damp = 1.0 + c;
@@ -233,17 +234,22 @@ k2b_point_solve_kernel(int64_t N, int M, int axis, const int64_t* __restrict__ o
     for (int64_t o0 = lo; o0 < hi; o0 += 32) {
       const int64_t o = o0 + lane;
       const int cnt = (int)(hi - o0 < 32 ? hi - o0 : 32);
-      if (o < hi) {
+      const bool on = o < hi;
+      // masked camera Jacobian rows (gauge-pinned parameters zeroed) and T = 2 Jx L^-T (2x3):
+      // T[k][d] = 2 sum_b Jx[k][b] m[d][b]
+      double ja[9], jb[9];
+      double ta0 = 0, ta1 = 0, ta2 = 0, tb0 = 0, tb1 = 0, tb2 = 0;
+      int mypos = 0;
+      if (on) {
         const int i = DENSE ? (int)(o - lo) : obs_cam[o];
         const uint32_t mask = gauge_mask(i, axis);
         const double2* rp = reinterpret_cast<const double2*>(JP + (size_t)o * kJP);
         const double2 p1 = rp[1], p2 = rp[2], p3 = rp[3];
         const double a0 = p1.x, a1 = p1.y, a2 = p2.x, b0 = p2.y, b1 = p3.x, b2 = p3.y;
-        // T = 2 Jx L^-T  (2x3): T[k][d] = 2 sum_b Jx[k][b] m[d][b]
-        const double ta0 = 2.0 * (a0 * m00), ta1 = 2.0 * (a0 * m10 + a1 * m11),
-                     ta2 = 2.0 * (a0 * m20 + a1 * m21 + a2 * m22);
-        const double tb0 = 2.0 * (b0 * m00), tb1 = 2.0 * (b0 * m10 + b1 * m11),
-                     tb2 = 2.0 * (b0 * m20 + b1 * m21 + b2 * m22);
+        ta0 = 2.0 * (a0 * m00); ta1 = 2.0 * (a0 * m10 + a1 * m11);
+        ta2 = 2.0 * (a0 * m20 + a1 * m21 + a2 * m22);
+        tb0 = 2.0 * (b0 * m00); tb1 = 2.0 * (b0 * m10 + b1 * m11);
+        tb2 = 2.0 * (b0 * m20 + b1 * m21 + b2 * m22);
         const double2* rc = reinterpret_cast<const double2*>(JC + (size_t)o * kJC);
         double jc[kJC];
 #pragma unroll
@@ -252,15 +258,48 @@ k2b_point_solve_kernel(int64_t N, int M, int axis, const int64_t* __restrict__ o
           jc[2 * k] = t2.x;
           jc[2 * k + 1] = t2.y;
         }
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+          const bool pin = (mask >> a) & 1u;
+          ja[a] = pin ? 0.0 : jc[2 + a];
+          jb[a] = pin ? 0.0 : jc[11 + a];
+        }
+        if (!DENSE) mypos = cm_pos[o];
+      }
+      if (!DENSE) {
+        // Factors of Y for the pair kernel (k3_schur_sparse.cu), camera-major: staged per lane,
+        // then 12 lanes x 16 B write one whole 192-byte block.
+        if (on) {
+          double* f = st + kYcm * lane;
+#pragma unroll
+          for (int a = 0; a < 9; ++a) {
+            f[a] = ja[a];
+            f[9 + a] = jb[a];
+          }
+          f[18] = ta0; f[19] = ta1; f[20] = ta2;
+          f[21] = tb0; f[22] = tb1; f[23] = tb2;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 12; ++u) {
+          const int p = lane + 32 * u;
+          const int blk = (p * 43691) >> 19;  // p / 12 for p < 768
+          const int piece = p - 12 * blk;
+          const int pos = __shfl_sync(0xffffffffu, mypos, blk);
+          if (blk < cnt)
+            *reinterpret_cast<double2*>(Ycm + (size_t)pos * kYcm + 2 * piece) =
+                *reinterpret_cast<const double2*>(st + kYcm * blk + 2 * piece);
+        }
+        __syncwarp();
+      }
+      if (on) {
         // Y[a][d] = Jc0[a] T[0][d] + Jc1[a] T[1][d], staged in shared memory so that the warp
         // writes whole contiguous runs (the per-lane 72-byte pieces would be partial sectors)
 #pragma unroll
         for (int a = 0; a < 9; ++a) {
-          const bool pin = (mask >> a) & 1u;
-          const double ja = pin ? 0.0 : jc[2 + a], jb = pin ? 0.0 : jc[11 + a];
-          const double y0 = ja * ta0 + jb * tb0;
-          const double y1 = ja * ta1 + jb * tb1;
-          const double y2 = ja * ta2 + jb * tb2;
+          const double y0 = ja[a] * ta0 + jb[a] * tb0;
+          const double y1 = ja[a] * ta1 + jb[a] * tb1;
+          const double y2 = ja[a] * ta2 + jb[a] * tb2;
           if (DENSE) {
             st[9 * lane + a] = y0;
             st[288 + 9 * lane + a] = y1;
@@ -302,11 +341,11 @@ int launch_k2b(ba_engine* e, bool conditional, double c_host, cudaStream_t s) {
   if (e->dense)
     k2b_point_solve_kernel<true><<<grid, 256, kStage, s>>>(
         e->N, e->M, e->axis, e->obs_ptr, e->obs_cam, e->JP, e->JC, e->V, e->GPT, c_host, e->ctl,
-        use_ctl, e->LINV, e->Z, e->Yt, e->n_pad, e->rhs_row, e->Ysp);
+        use_ctl, e->LINV, e->Z, e->Yt, e->n_pad, e->rhs_row, e->Ysp, e->cm_pos, e->Ycm);
   else
     k2b_point_solve_kernel<false><<<grid, 256, kStage, s>>>(
         e->N, e->M, e->axis, e->obs_ptr, e->obs_cam, e->JP, e->JC, e->V, e->GPT, c_host, e->ctl,
-        use_ctl, e->LINV, e->Z, e->Yt, e->n_pad, e->rhs_row, e->Ysp);
+        use_ctl, e->LINV, e->Z, e->Yt, e->n_pad, e->rhs_row, e->Ysp, e->cm_pos, e->Ycm);
   BA_LAUNCH_CHECK();
   return BA_OK;
 }
