@@ -209,7 +209,7 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
     A(dev_alloc(&e->cm_perm, (size_t)e->nobs));
     A(dev_alloc(&e->cam_ptr, (size_t)e->M + 1));
     A(dev_alloc(&e->cm_pos, (size_t)e->nobs));
-    e->Wp = round_up64((e->N + 31) / 32, 32);
+    e->Wp = round_up64((e->N + 31) / 32, 64);
     A(dev_alloc(&e->bitpre, (size_t)e->M * e->Wp));
   }
   for (int w = 0; w < 2; ++w) {

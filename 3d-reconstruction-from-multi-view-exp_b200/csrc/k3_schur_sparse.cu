@@ -85,9 +85,8 @@ int build_pair_index(ba_engine* e, cudaStream_t s) {
 }
 
 // ---- off-diagonal pairs -------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gmem));
 }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
@@ -96,7 +95,6 @@ __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0
 // Pair number t -> (i, k), k < i.  Pairs are ordered tile by tile (kPairTile x kPairTile cameras),
 // so that the warps resident at any time share few camera slices and walk them in step (L2 reuse).
 __device__ __forceinline__ bool pair_from_linear(int64_t t, int M, int& i, int& k) {
-  const int nt = (M + kPairTile - 1) / kPairTile;
   const int64_t per_tile = (int64_t)kPairTile * kPairTile;
   const int64_t tile = t / per_tile;
   const int r = (int)(t - tile * per_tile);
@@ -104,7 +102,6 @@ __device__ __forceinline__ bool pair_from_linear(int64_t t, int M, int& i, int& 
   while ((int64_t)(ti + 1) * (ti + 2) / 2 <= tile) ++ti;
   while ((int64_t)ti * (ti + 1) / 2 > tile) --ti;
   const int tk = (int)(tile - (int64_t)ti * (ti + 1) / 2);
-  (void)nt;
   i = ti * kPairTile + r / kPairTile;
   k = tk * kPairTile + r % kPairTile;
   return i < M && k < i;
@@ -112,7 +109,7 @@ __device__ __forceinline__ bool pair_from_linear(int64_t t, int M, int& i, int& 
 
 struct PairSmem {
   double stage[2][64 * kYS];  // [stage][block: 0..31 camera i side, 32..63 camera k side][kYS]
-  uint2 queue[64];            // ring of (position in slice i, position in slice k)
+  uint2 queue[64];            // (position in slice i, position in slice k); [0, 32) = the next round
 };
 
 __global__ void __launch_bounds__(32, 8)
@@ -124,17 +121,19 @@ schur_pairs_kernel(int M, int64_t Wp, const uint2* __restrict__ bitpre,
   if (!pair_from_linear(blockIdx.x, M, i, k)) return;
   __shared__ __align__(16) PairSmem sm;
   const int lane = threadIdx.x;
-  const uint32_t lt_mask = (1u << lane) - 1u;
 
-  const uint2* bi = bitpre + (size_t)i * Wp;
-  const uint2* bk = bitpre + (size_t)k * Wp;
-  const double* Yi = Ycm + (size_t)cam_ptr[i] * kYB;
-  const double* Yk = Ycm + (size_t)cam_ptr[k] * kYB;
-
-  // gather mapping: lanes 0..11 copy the 12 pieces of one block, lanes 12..23 of the next one
+  // two bitmap words (64 points) per lane and batch
+  const uint4* bi = reinterpret_cast<const uint4*>(bitpre + (size_t)i * Wp) + lane;
+  const uint4* bk = reinterpret_cast<const uint4*>(bitpre + (size_t)k * Wp) + lane;
+  // gather mapping: lanes 0..11 copy the 12 pieces of one block, lanes 12..23 of the next one;
+  // the piece offset is folded into the base pointers
   const int g_sub = lane >= 12 ? 1 : 0;
   const int g_piece = lane - 12 * g_sub;
   const bool g_on = lane < 24;
+  const double* Yi = Ycm + (size_t)cam_ptr[i] * kYB + 2 * g_piece;
+  const double* Yk = Ycm + (size_t)cam_ptr[k] * kYB + 2 * g_piece;
+  const uint32_t q_addr = (uint32_t)__cvta_generic_to_shared(sm.queue) + 8u * g_sub;
+  const uint32_t s_addr = (uint32_t)__cvta_generic_to_shared(sm.stage[0]) + (g_sub * kYS + 2 * g_piece) * 8u;
 
   double acc[9][9];
 #pragma unroll
@@ -142,7 +141,7 @@ schur_pairs_kernel(int M, int64_t Wp, const uint2* __restrict__ bitpre,
 #pragma unroll
     for (int b = 0; b < 9; ++b) acc[a][b] = 0.0;
 
-  int qh = 0, qn = 0;   // queue head, entries queued
+  int qn = 0;           // entries queued
   int rounds = 0;       // rounds whose gather has been issued
   int cnt_prev = 0;     // valid lanes of the round waiting in stage (rounds - 1) & 1
 
@@ -191,52 +190,76 @@ schur_pairs_kernel(int M, int64_t Wp, const uint2* __restrict__ bitpre,
     }
   };
 
-  // Issue the gather of the next round (up to 32 queued entries), then compute the previous one.
+  // Issue the gather of the next round (queue[0, cnt)), move the rest of the queue down, then
+  // compute the previous round.
   auto round = [&](int cnt) {
-    const int st = rounds & 1;
-#pragma unroll 4
-    for (int u = 0; u < 16; ++u) {
-      const int b = 2 * u + g_sub;  // entry of the round
-      if (g_on && b < cnt) {
-        const uint2 en = sm.queue[(qh + b) & 63];
-        cp_async16(sm.stage[st] + b * kYS + 2 * g_piece, Yi + (size_t)en.x * kYB + 2 * g_piece);
-        cp_async16(sm.stage[st] + (32 + b) * kYS + 2 * g_piece, Yk + (size_t)en.y * kYB + 2 * g_piece);
+    const uint32_t sa = s_addr + (uint32_t)(rounds & 1) * (64 * kYS * 8);
+    if (cnt == 32) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        uint2 en;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(en.x), "=r"(en.y) : "r"(q_addr + 16u * u));
+        if (g_on) {
+          cp_async16(sa + 2 * u * kYS * 8, Yi + (size_t)en.x * kYB);
+          cp_async16(sa + (32 + 2 * u) * kYS * 8, Yk + (size_t)en.y * kYB);
+        }
+      }
+    } else {
+      for (int u = 0; 2 * u < cnt; ++u) {
+        const uint2 en = sm.queue[2 * u + g_sub];
+        if (g_on && 2 * u + g_sub < cnt) {
+          cp_async16(sa + 2 * u * kYS * 8, Yi + (size_t)en.x * kYB);
+          cp_async16(sa + (32 + 2 * u) * kYS * 8, Yk + (size_t)en.y * kYB);
+        }
       }
     }
     cp_commit();
-    qh = (qh + cnt) & 63;
     qn -= cnt;
+    {
+      const uint2 up = sm.queue[32 + lane];
+      __syncwarp();
+      sm.queue[lane] = up;
+    }
     if (rounds > 0) {
       cp_wait<1>();
       __syncwarp();
-      compute(st ^ 1, cnt_prev);
-      __syncwarp();
+      compute((rounds & 1) ^ 1, cnt_prev);
     }
+    __syncwarp();
     cnt_prev = cnt;
     ++rounds;
   };
 
   // bitmap words are fetched one batch ahead
-  uint2 wi = bi[lane], wk = bk[lane];
-  for (int64_t w0 = 0; w0 < Wp; w0 += 32) {
-    const uint2 ci = wi, ck = wk;
-    if (w0 + 32 < Wp) {
-      wi = bi[w0 + 32 + lane];
-      wk = bk[w0 + 32 + lane];
+  uint4 wi = bi[0], wk = bk[0];
+  for (int64_t w0 = 0; w0 < Wp; w0 += 64) {
+    const uint4 ci = wi, ck = wk;
+    if (w0 + 64 < Wp) {
+      wi = bi[(w0 + 64) >> 1];
+      wk = bk[(w0 + 64) >> 1];
     }
-    uint32_t c = ci.x & ck.x;
-    uint32_t any;
-    while ((any = __ballot_sync(0xffffffffu, c != 0u)) != 0u) {
-      if (c) {
-        const int b = __ffs(c) - 1;
-        c &= c - 1;
-        const uint32_t below = (1u << b) - 1u;
-        const int pos = qn + __popc(any & lt_mask);
-        sm.queue[(qh + pos) & 63] = make_uint2(ci.y + __popc(ci.x & below), ck.y + __popc(ck.x & below));
+    const uint64_t mi = ((uint64_t)ci.z << 32) | ci.x, mk = ((uint64_t)ck.z << 32) | ck.x;
+    uint64_t c = mi & mk;
+    while (__any_sync(0xffffffffu, c != 0ull)) {
+      // exclusive prefix of the hit counts -> queue slots; hits that do not fit wait for the next pass
+      const int n = __popcll(c);
+      int incl = n;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
       }
-      qn += __popc(any);
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int pos = qn + incl - n;
+      while (c != 0ull && pos < 64) {
+        const int b = __ffsll((long long)c) - 1;
+        c &= c - 1;
+        const uint64_t below = (1ull << b) - 1ull;
+        sm.queue[pos++] = make_uint2(ci.y + __popcll(mi & below), ck.y + __popcll(mk & below));
+      }
+      qn = qn + total < 64 ? qn + total : 64;
       __syncwarp();
-      if (qn >= 32) round(32);
+      while (qn >= 32) round(32);
     }
   }
   if (qn > 0) round(qn);
