@@ -40,8 +40,8 @@ constexpr int kCamTab = 16;   // doubles per camera in the derived table (128 B 
 constexpr int kJP = 8;        // doubles per observation, point-side row: e(2), de/dX (2x3)
 constexpr int kJC = 20;       // doubles per observation, camera-side row: e(2), de/dcam (2x9)
 constexpr int kUPart = 54;    // 45 unique entries of U_i + 9 of dF_i
-constexpr int kYcm = 24;      // doubles per observation in the camera-major factor array (sparse):
-                              // Jc row 0 (9), Jc row 1 (9), T = 2 Jx L^-T rows 0 and 1 (3 + 3)
+constexpr int kPT = 12;       // doubles per point in the pair kernel's point table (sparse):
+                              // X (3), damped V^-1 (00 01 02 11 12 22), 3 pad = 96 B = 3 sectors
 constexpr int kCholNB = 64;   // panel width of the blocked Cholesky
 constexpr int kMaxRecords = 4096;
 
@@ -91,9 +91,8 @@ struct ba_engine {
   double* obs_xy = nullptr;
   int64_t* cam_ptr = nullptr;  // [M+1] (sparse)
   int32_t* cm_perm = nullptr;  // [nobs] observation ids sorted by camera (sparse)
-  int32_t* cm_pos = nullptr;   // [nobs] inverse of cm_perm: position of an observation in its camera's slice order (sparse)
-  uint2* bitpre = nullptr;     // [M][Wp] per camera: .x = bitmap word over points, .y = set bits in earlier words (sparse)
-  int64_t Wp = 0;              // words per camera bitmap, padded to a multiple of 32
+  uint32_t* bits = nullptr;    // [M][Wp] per camera: bitmap over points (sparse)
+  int64_t Wp = 0;              // words per camera bitmap, padded to a multiple of 128
   bool have_obs = false, have_state = false;
 
   // state: [0] current, [1] trial
@@ -111,7 +110,7 @@ struct ba_engine {
   double *LINV = nullptr, *Z = nullptr;
   double* Yt = nullptr;   // dense: [k_pad][n_pad]
   double* Ysp = nullptr;  // sparse: [nobs][27]
-  double* Ycm = nullptr;  // sparse: [nobs][kYcm] camera-major factors of Y (operand of the pair kernel)
+  double* PT = nullptr;   // sparse: [N][kPT] point table of the pair kernel (X, damped V^-1)
   double* red = nullptr;  // [n_pad*n_pad | M*81 | M*9]
   int64_t red_len = 0;
   double* Spart = nullptr;  // split-K partial tiles

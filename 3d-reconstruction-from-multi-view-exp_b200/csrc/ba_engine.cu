@@ -123,7 +123,7 @@ int build_camera_major_index(ba_engine* e, cudaStream_t s) {
 static void free_engine(ba_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  void* ptrs[] = {e->obs_ptr, e->obs_cam, e->obs_pt, e->obs_xy, e->cam_ptr, e->cm_perm, e->cm_pos, e->bitpre, e->Ycm, e->X[0],
+  void* ptrs[] = {e->obs_ptr, e->obs_cam, e->obs_pt, e->obs_xy, e->cam_ptr, e->cm_perm, e->bits, e->PT, e->X[0],
                   e->X[1], e->cam[0].f, e->cam[1].f, e->camtab[0], e->camtab[1], e->JP, e->JC, e->V,
                   e->GPT, e->Upart, e->Uloc, e->LINV, e->Z, e->Yt, e->Ysp, e->red, e->Spart, e->Lt, e->Winv,
                   e->dxi, e->cost_part, e->cost_buf, e->ctl, e->rec};
@@ -208,9 +208,9 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
     A(dev_alloc(&e->obs_pt, (size_t)e->nobs));
     A(dev_alloc(&e->cm_perm, (size_t)e->nobs));
     A(dev_alloc(&e->cam_ptr, (size_t)e->M + 1));
-    A(dev_alloc(&e->cm_pos, (size_t)e->nobs));
-    e->Wp = round_up64((e->N + 31) / 32, 64);
-    A(dev_alloc(&e->bitpre, (size_t)e->M * e->Wp));
+    e->Wp = round_up64((e->N + 31) / 32, 128);
+    A(dev_alloc(&e->bits, (size_t)e->M * e->Wp));
+    A(dev_alloc(&e->PT, (size_t)e->N * kPT));
   }
   for (int w = 0; w < 2; ++w) {
     A(dev_alloc(&e->X[w], (size_t)3 * e->N));
@@ -233,7 +233,6 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
     A(dev_alloc(&e->Spart, (size_t)e->syrk_splits * (nt1 * (nt1 + 1) / 2) * e->syrk_tile * e->syrk_tile));
   } else {
     A(dev_alloc(&e->Ysp, (size_t)e->nobs * 27));
-    A(dev_alloc(&e->Ycm, (size_t)e->nobs * kYcm));
   }
   A(dev_alloc(&e->Lt, (size_t)kCholNB * e->n_pad));
   A(dev_alloc(&e->Winv, (size_t)((e->n_full + kCholNB - 1) / kCholNB) * kCholNB * kCholNB));

@@ -184,7 +184,7 @@ k2b_point_solve_kernel(int64_t N, int M, int axis, const int64_t* __restrict__ o
                        const double* __restrict__ GPT, double c_host, ba_lm_state* ctl,
                        int use_ctl, double* __restrict__ LINV, double* __restrict__ Z,
                        double* __restrict__ Yt, int ld, int rhs_col, double* __restrict__ Ysp,
-                       const int32_t* __restrict__ cm_pos, double* __restrict__ Ycm) {
+                       const double* __restrict__ X, double* __restrict__ PT) {
   if (use_ctl && ctl->done) return;
   const double c = use_ctl ? ctl->c : c_host;
   const double damp = 1.0 + c;
@@ -223,6 +223,19 @@ k2b_point_solve_kernel(int64_t N, int M, int axis, const int64_t* __restrict__ o
       li[0] = m00; li[1] = m10; li[2] = m11; li[3] = m20; li[4] = m21; li[5] = m22;
       double* z = Z + 3 * (size_t)j;
       z[0] = z0; z[1] = z1; z[2] = z2;
+      if (!DENSE) {
+        // point table of the pair kernel: X_j and the damped inverse block V^-1 = L^-T L^-1
+        double* pt = PT + (size_t)j * kPT;
+        pt[0] = X[3 * (size_t)j];
+        pt[1] = X[3 * (size_t)j + 1];
+        pt[2] = X[3 * (size_t)j + 2];
+        pt[3] = m00 * m00 + m10 * m10 + m20 * m20;
+        pt[4] = m10 * m11 + m20 * m21;
+        pt[5] = m20 * m22;
+        pt[6] = m11 * m11 + m21 * m21;
+        pt[7] = m21 * m22;
+        pt[8] = m22 * m22;
+      }
       if (DENSE) {
         Yt[(size_t)(3 * j + 0) * ld + rhs_col] = z0;
         Yt[(size_t)(3 * j + 1) * ld + rhs_col] = z1;
@@ -239,7 +252,6 @@ k2b_point_solve_kernel(int64_t N, int M, int axis, const int64_t* __restrict__ o
       // T[k][d] = 2 sum_b Jx[k][b] m[d][b]
       double ja[9], jb[9];
       double ta0 = 0, ta1 = 0, ta2 = 0, tb0 = 0, tb1 = 0, tb2 = 0;
-      int mypos = 0;
       if (on) {
         const int i = DENSE ? (int)(o - lo) : obs_cam[o];
         const uint32_t mask = gauge_mask(i, axis);
@@ -264,33 +276,6 @@ k2b_point_solve_kernel(int64_t N, int M, int axis, const int64_t* __restrict__ o
           ja[a] = pin ? 0.0 : jc[2 + a];
           jb[a] = pin ? 0.0 : jc[11 + a];
         }
-        if (!DENSE) mypos = cm_pos[o];
-      }
-      if (!DENSE) {
-        // Factors of Y for the pair kernel (k3_schur_sparse.cu), camera-major: staged per lane,
-        // then 12 lanes x 16 B write one whole 192-byte block.
-        if (on) {
-          double* f = st + kYcm * lane;
-#pragma unroll
-          for (int a = 0; a < 9; ++a) {
-            f[a] = ja[a];
-            f[9 + a] = jb[a];
-          }
-          f[18] = ta0; f[19] = ta1; f[20] = ta2;
-          f[21] = tb0; f[22] = tb1; f[23] = tb2;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int u = 0; u < 12; ++u) {
-          const int p = lane + 32 * u;
-          const int blk = (p * 43691) >> 19;  // p / 12 for p < 768
-          const int piece = p - 12 * blk;
-          const int pos = __shfl_sync(0xffffffffu, mypos, blk);
-          if (blk < cnt)
-            *reinterpret_cast<double2*>(Ycm + (size_t)pos * kYcm + 2 * piece) =
-                *reinterpret_cast<const double2*>(st + kYcm * blk + 2 * piece);
-        }
-        __syncwarp();
       }
       if (on) {
         // Y[a][d] = Jc0[a] T[0][d] + Jc1[a] T[1][d], staged in shared memory so that the warp
@@ -341,11 +326,11 @@ int launch_k2b(ba_engine* e, bool conditional, double c_host, cudaStream_t s) {
   if (e->dense)
     k2b_point_solve_kernel<true><<<grid, 256, kStage, s>>>(
         e->N, e->M, e->axis, e->obs_ptr, e->obs_cam, e->JP, e->JC, e->V, e->GPT, c_host, e->ctl,
-        use_ctl, e->LINV, e->Z, e->Yt, e->n_pad, e->rhs_row, e->Ysp, e->cm_pos, e->Ycm);
+        use_ctl, e->LINV, e->Z, e->Yt, e->n_pad, e->rhs_row, e->Ysp, e->X[0], e->PT);
   else
     k2b_point_solve_kernel<false><<<grid, 256, kStage, s>>>(
         e->N, e->M, e->axis, e->obs_ptr, e->obs_cam, e->JP, e->JC, e->V, e->GPT, c_host, e->ctl,
-        use_ctl, e->LINV, e->Z, e->Yt, e->n_pad, e->rhs_row, e->Ysp, e->cm_pos, e->Ycm);
+        use_ctl, e->LINV, e->Z, e->Yt, e->n_pad, e->rhs_row, e->Ysp, e->X[0], e->PT);
   BA_LAUNCH_CHECK();
   return BA_OK;
 }

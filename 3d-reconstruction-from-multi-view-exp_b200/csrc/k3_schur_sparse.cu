@@ -1,85 +1,58 @@
-// K3 for sparse visibility: pair-stationary Schur products, accumulators in registers.
+// K3 for sparse visibility: matrix-free, pair-stationary Schur products.
 //
 //   P[9i+a][9k+b] = sum over points j seen by both camera i and camera k (k <= i) of
 //                   sum_d Y_ij[a][d] Y_kj[b][d]                (reference :132-135)
 //   P[rhs][9i+a]  = sum_j sum_d Y_ij[a][d] z_j[d]               (reference :138-143)
 //
-// With Y_ij = Jc_ij^T T_ij (Jc the 2x9 camera Jacobian, T = 2 Jx L_j^-T the 2x3 point factor, both
-// written by K2b into the camera-major array Ycm[q][24] = [Jc row 0 | Jc row 1 | T row 0 | T row 1])
-// the pair product factors through a 2x2 matrix:
-//   Y_ij Y_kj^T = Jc_ij^T (T_ij T_kj^T) Jc_kj      -- 210 instead of 243 FMAs, 192 instead of 216 B.
+// With Y_ij = Jc_ij^T (2 Jx_ij) L_j^-T (Jc the 2x9 camera Jacobian, Jx the 2x3 point Jacobian of
+// observation (i, j), L_j L_j^T the damped V_j) the product of a camera pair through point j is
+//
+//   Y_ij Y_kj^T = Jc_ij^T G Jc_kj,    G = 4 Jx_ij Vd_j^-1 Jx_kj^T   (2x2),
+//
+// and Jc, Jx are functions of the camera parameters and X_j alone (reference :309-398; they do not
+// involve the observed image point).  So nothing per observation has to be read: the kernel
+// re-derives both Jacobians from the two cameras' table rows (shared memory) and the per-point row
+// PT[j] = [X_j | Vd_j^-1] (96 B; 96 MB for 10^6 points: resident in the 126 MB L2), i.e. ~310 FP64
+// operations and 96 B of L2 traffic per pair-point instead of 2 x 216 B of gathered Y blocks,
+// which at C4 (19 GB of blocks, each read m_j = 100 times) made the kernel latency/HBM bound.
 //
 // schur_pairs_kernel: ONE WARP PER CAMERA PAIR (i, k), k < i.  The warp intersects the two cameras'
-// point bitmaps 32 words at a time; a hit's position in either camera's slice of Ycm is the prefix
-// count stored next to the bitmap word (+ a popc).  Hits are queued; every 32 hits make a round:
-// the 64 blocks of the round are gathered into shared memory with 16-byte cp.async (12 lanes per
-// block: whole sectors), double buffered so the gather of round r+1 is in flight while round r is
-// computed; then every lane takes ONE common point and accumulates its 9x9 contribution into 81
-// registers.  There is no shared-memory or global read-modify-write at all; the accumulators meet
-// once per pair in a fixed-order butterfly.  Order of summation depends on the data only: runs
-// are bit-reproducible.
+// point bitmaps 4096 points at a time (128 bits per lane); hits (point ids) are compacted into a
+// queue with a warp prefix sum; every 32 hits make a round: the 32 point rows are gathered into
+// shared memory with 16-byte cp.async (6 lanes per row: whole sectors), double buffered so the
+// gather of round r+1 is in flight while round r is computed; then every lane takes ONE common
+// point and accumulates its 9x9 contribution into 81 registers.  No shared-memory or global
+// read-modify-write at all; the accumulators meet once per pair in a fixed-order butterfly.
+// Order of summation depends on the data only: runs are bit-reproducible.
 //
-// Bound: every pair-point moves 2 x 192 B from L2 to the SM for 210 FMAs, i.e. the kernel is bound
-// by L2 -> SM bandwidth (the Y blocks of C4 are 19 GB, each read m_j = 100 times), not by FP64.
+// Bound: FP64 pipe (310 operations per pair-point; sum_j m_j (m_j - 1) / 2 pair-points).
 //
 // schur_diag_kernel: the diagonal blocks P[9i..][9i..] and the rhs row, a segmented reduction over
-// the camera's contiguous slice of Ycm (fixed chunking and order).
+// the camera's observations in camera-major order (fixed chunking and order).
 #include "ba_common.cuh"
 
 namespace ba {
 
-constexpr int kYB = kYcm;          // doubles per block in Ycm (24 = 192 B)
-constexpr int kYS = 26;            // doubles per block in shared memory (208 B = 13 x 16: odd -> conflict-free LDS.128)
+constexpr int kPS = 14;            // doubles per point row in shared memory (112 B = 7 x 16: odd -> conflict-free LDS.128)
 constexpr int kPairTile = 32;      // pairs are scheduled in kPairTile x kPairTile tiles of (i, k)
 constexpr int kDiagPart = 54;      // 45 unique entries of the diagonal block + 9 rhs entries
+constexpr int kQueue = 128;        // queue capacity (point ids)
+constexpr int kFragX = 32 * 8 + 4; // doubles between the two rows of a fragment array (+4: conflict-free fragment loads)
 
-// ---- index: per camera bitmap over points + running prefix count --------------------------------
+// ---- index: per camera bitmap over points -------------------------------------------------------
 __global__ void bitmap_fill_kernel(int64_t nobs, int64_t Wp, const int32_t* __restrict__ obs_cam,
-                                   const int32_t* __restrict__ obs_pt, uint2* __restrict__ bitpre) {
+                                   const int32_t* __restrict__ obs_pt, uint32_t* __restrict__ bits) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < nobs; o += stride) {
     const int j = obs_pt[o];
-    atomicOr(&bitpre[(size_t)obs_cam[o] * Wp + (j >> 5)].x, 1u << (j & 31));
+    atomicOr(&bits[(size_t)obs_cam[o] * Wp + (j >> 5)], 1u << (j & 31));
   }
-}
-
-// One block per camera: y = number of set bits in the words before this one.
-__global__ void __launch_bounds__(1024)
-bitmap_prefix_kernel(int64_t Wp, uint2* __restrict__ bitpre) {
-  __shared__ uint32_t part[1024];
-  uint2* row = bitpre + (size_t)blockIdx.x * Wp;
-  const int64_t per = (Wp + 1023) / 1024;
-  const int64_t lo = per * threadIdx.x, hi = lo + per < Wp ? lo + per : Wp;
-  uint32_t s = 0;
-  for (int64_t w = lo; w < hi; ++w) s += __popc(row[w].x);
-  part[threadIdx.x] = s;
-  __syncthreads();
-  // Hillis-Steele inclusive scan over the 1024 partial counts
-  for (int off = 1; off < 1024; off <<= 1) {
-    const uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
-    __syncthreads();
-    part[threadIdx.x] += v;
-    __syncthreads();
-  }
-  uint32_t run = part[threadIdx.x] - s;
-  for (int64_t w = lo; w < hi; ++w) {
-    row[w].y = run;
-    run += __popc(row[w].x);
-  }
-}
-
-__global__ void invert_perm_kernel(int64_t n, const int32_t* __restrict__ perm, int32_t* __restrict__ inv) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride) inv[perm[q]] = (int32_t)q;
 }
 
 int build_pair_index(ba_engine* e, cudaStream_t s) {
-  BA_CUDA(cudaMemsetAsync(e->bitpre, 0, (size_t)e->M * e->Wp * sizeof(uint2), s));
-  bitmap_fill_kernel<<<e->num_sms * 8, 256, 0, s>>>(e->nobs, e->Wp, e->obs_cam, e->obs_pt, e->bitpre);
-  BA_LAUNCH_CHECK();
-  bitmap_prefix_kernel<<<e->M, 1024, 0, s>>>(e->Wp, e->bitpre);
-  BA_LAUNCH_CHECK();
-  invert_perm_kernel<<<e->num_sms * 8, 256, 0, s>>>(e->nobs, e->cm_perm, e->cm_pos);
+  BA_CUDA(cudaMemsetAsync(e->bits, 0, (size_t)e->M * e->Wp * sizeof(uint32_t), s));
+  BA_CUDA(cudaMemsetAsync(e->PT, 0, (size_t)e->N * kPT * sizeof(double), s));
+  bitmap_fill_kernel<<<e->num_sms * 8, 256, 0, s>>>(e->nobs, e->Wp, e->obs_cam, e->obs_pt, e->bits);
   BA_LAUNCH_CHECK();
   return BA_OK;
 }
@@ -93,7 +66,7 @@ template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // Pair number t -> (i, k), k < i.  Pairs are ordered tile by tile (kPairTile x kPairTile cameras),
-// so that the warps resident at any time share few camera slices and walk them in step (L2 reuse).
+// so that the warps resident at any time share few bitmaps and walk the points in step.
 __device__ __forceinline__ bool pair_from_linear(int64_t t, int M, int& i, int& k) {
   const int64_t per_tile = (int64_t)kPairTile * kPairTile;
   const int64_t tile = t / per_tile;
@@ -108,13 +81,43 @@ __device__ __forceinline__ bool pair_from_linear(int64_t t, int M, int& i, int& 
 }
 
 struct PairSmem {
-  double stage[2][64 * kYS];  // [stage][block: 0..31 camera i side, 32..63 camera k side][kYS]
-  uint2 queue[64];            // (position in slice i, position in slice k); [0, 32) = the next round
+  double stage[2][32 * kPS];  // [stage][point of the round][kPS]: X (3), Vd^-1 (6: 00 01 02 11 12 22)
+  double cam[2][20];          // table rows of camera i and k (K1's layout) + 1/f, u0/f0, v0/f0, 1/f0
+  double ifrag[2 * kFragX];   // [x][lane][8]: first 8 entries of Jc_i row x of the lane's point (DMMA A operand)
+  double tfrag[2 * kFragX];   // [x][lane][8]: first 8 entries of row x of G Jc_k            (DMMA B operand)
+  int32_t queue[kQueue];      // point ids; [0, 32) = the next round
 };
 
-__global__ void __launch_bounds__(32, 8)
-schur_pairs_kernel(int M, int64_t Wp, const uint2* __restrict__ bitpre,
-                   const int64_t* __restrict__ cam_ptr, const double* __restrict__ Ycm,
+// Unscaled Jacobian pieces of one camera at one point (K1's formulas without the 1/r^2 factor):
+// camera row a = [af, au, 0, -aX, aX x d], row b = [bf, 0, au, -bX, bX x d]; point rows aX, bX.
+struct SideJac {
+  double aX[3], bX[3], d[3], af, bf, au, r;
+};
+
+__device__ __forceinline__ SideJac side_jacobian(const double* __restrict__ c, double x0, double x1,
+                                                 double x2) {
+  SideJac s;
+  s.d[0] = x0 - c[9];
+  s.d[1] = x1 - c[10];
+  s.d[2] = x2 - c[11];
+  const double p = c[0] * s.d[0] + c[1] * s.d[1] + c[2] * s.d[2];
+  const double q = c[3] * s.d[0] + c[4] * s.d[1] + c[5] * s.d[2];
+  const double r = c[6] * s.d[0] + c[7] * s.d[1] + c[8] * s.d[2];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    s.aX[m] = r * c[m] - p * c[6 + m];      // :450
+    s.bX[m] = r * c[3 + m] - q * c[6 + m];  // :459
+  }
+  s.af = r * ((p - c[17] * r) * c[16]);  // :336  (c[16] = 1/f, c[17] = u0/f0)
+  s.bf = r * ((q - c[18] * r) * c[16]);  // :337  (c[18] = v0/f0)
+  s.au = r * (r * c[19]);                // :350-356 (c[19] = 1/f0)
+  s.r = r;
+  return s;
+}
+
+__global__ void __launch_bounds__(32, 12)
+schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bits,
+                   const double* __restrict__ camtab, double f0, const double* __restrict__ PT,
                    double* __restrict__ P, int ld, const ba_lm_state* ctl) {
   if (ctl && ctl->done) return;
   int i, k;
@@ -122,103 +125,163 @@ schur_pairs_kernel(int M, int64_t Wp, const uint2* __restrict__ bitpre,
   __shared__ __align__(16) PairSmem sm;
   const int lane = threadIdx.x;
 
-  // two bitmap words (64 points) per lane and batch
-  const uint4* bi = reinterpret_cast<const uint4*>(bitpre + (size_t)i * Wp) + lane;
-  const uint4* bk = reinterpret_cast<const uint4*>(bitpre + (size_t)k * Wp) + lane;
-  // gather mapping: lanes 0..11 copy the 12 pieces of one block, lanes 12..23 of the next one;
-  // the piece offset is folded into the base pointers
-  const int g_sub = lane >= 12 ? 1 : 0;
-  const int g_piece = lane - 12 * g_sub;
-  const bool g_on = lane < 24;
-  const double* Yi = Ycm + (size_t)cam_ptr[i] * kYB + 2 * g_piece;
-  const double* Yk = Ycm + (size_t)cam_ptr[k] * kYB + 2 * g_piece;
-  const uint32_t q_addr = (uint32_t)__cvta_generic_to_shared(sm.queue) + 8u * g_sub;
-  const uint32_t s_addr = (uint32_t)__cvta_generic_to_shared(sm.stage[0]) + (g_sub * kYS + 2 * g_piece) * 8u;
+  {
+    const int which = lane >> 4, c = lane & 15;
+    const double v = camtab[(size_t)(which ? k : i) * kCamTab + c];
+    sm.cam[which][c] = v;
+    __syncwarp();
+    if (c == 0) {
+      const double f = sm.cam[which][12], u0 = sm.cam[which][13], v0 = sm.cam[which][14];
+      sm.cam[which][16] = 1.0 / f;
+      sm.cam[which][17] = u0 / f0;
+      sm.cam[which][18] = v0 / f0;
+      sm.cam[which][19] = 1.0 / f0;
+    }
+    __syncwarp();
+  }
 
-  double acc[9][9];
+  // four bitmap words (128 points) per lane and batch
+  const uint4* bi = reinterpret_cast<const uint4*>(bits + (size_t)i * Wp) + lane;
+  const uint4* bk = reinterpret_cast<const uint4*>(bits + (size_t)k * Wp) + lane;
+  const uint32_t q_addr = (uint32_t)__cvta_generic_to_shared(sm.queue);
+  const uint32_t s_addr = (uint32_t)__cvta_generic_to_shared(sm.stage[0]);
+
+  // Accumulators.  The 8x8 leading part of the block is summed over the 32 lanes' points by the
+  // FP64 tensor cores (DMMA.8x8x4, K = 2 rows x 32 points per round): 2 registers per lane in the
+  // m8n8 C-fragment layout (row lane / 4, columns 2 (lane % 4) + {0, 1}).  Row 8, column 8 and the
+  // corner stay per lane and meet in a fixed-order butterfly at the end.
+  double c0 = 0.0, c1 = 0.0;
+  double r8[8], c8[8], c88 = 0.0;
 #pragma unroll
-  for (int a = 0; a < 9; ++a)
-#pragma unroll
-    for (int b = 0; b < 9; ++b) acc[a][b] = 0.0;
+  for (int a = 0; a < 8; ++a) r8[a] = c8[a] = 0.0;
+  const int fg = lane >> 2, fkq = lane & 3;
+  const int frag_base = (fkq & 1) * kFragX + (fkq >> 1) * 8;
 
   int qn = 0;           // entries queued
   int rounds = 0;       // rounds whose gather has been issued
   int cnt_prev = 0;     // valid lanes of the round waiting in stage (rounds - 1) & 1
 
   auto compute = [&](int st, int cnt) {
+    double2* i0 = reinterpret_cast<double2*>(sm.ifrag + lane * 8);
+    double2* i1 = reinterpret_cast<double2*>(sm.ifrag + kFragX + lane * 8);
+    double2* t0s = reinterpret_cast<double2*>(sm.tfrag + lane * 8);
+    double2* t1s = reinterpret_cast<double2*>(sm.tfrag + kFragX + lane * 8);
+    const int sw = (lane >> 1) & 3;
     if (lane < cnt) {
-      const double* pi = sm.stage[st] + lane * kYS;
-      const double* pk = sm.stage[st] + (32 + lane) * kYS;
-      const double2 ti0 = *reinterpret_cast<const double2*>(pi + 18);  // Ti row 0: [0], [1]
-      const double2 ti1 = *reinterpret_cast<const double2*>(pi + 20);  // Ti[0][2], Ti[1][0]
-      const double2 ti2 = *reinterpret_cast<const double2*>(pi + 22);  // Ti[1][1], Ti[1][2]
-      const double2 tk0 = *reinterpret_cast<const double2*>(pk + 18);
-      const double2 tk1 = *reinterpret_cast<const double2*>(pk + 20);
-      const double2 tk2 = *reinterpret_cast<const double2*>(pk + 22);
-      // G = Ti Tk^T (2x2)
-      const double g00 = ti0.x * tk0.x + ti0.y * tk0.y + ti1.x * tk1.x;
-      const double g01 = ti0.x * tk1.y + ti0.y * tk2.x + ti1.x * tk2.y;
-      const double g10 = ti1.y * tk0.x + ti2.x * tk0.y + ti2.y * tk1.x;
-      const double g11 = ti1.y * tk1.y + ti2.x * tk2.x + ti2.y * tk2.y;
-      // rows of G Jc_k (2x9)
+      const double* pt = sm.stage[st] + lane * kPS;
+      const double2 x01 = *reinterpret_cast<const double2*>(pt);
+      const double2 x2v = *reinterpret_cast<const double2*>(pt + 2);  // X2, V00
+      const double2 v12 = *reinterpret_cast<const double2*>(pt + 4);  // V01, V02
+      const double2 v34 = *reinterpret_cast<const double2*>(pt + 6);  // V11, V12
+      const double v22 = pt[8];
+      const double v00 = x2v.y, v01 = v12.x, v02 = v12.y, v11 = v34.x, v12_ = v34.y;
+      const SideJac si = side_jacobian(sm.cam[0], x01.x, x01.y, x2v.x);
       double t0[9], t1[9];
       {
-        double jk[18];
+        const SideJac sk = side_jacobian(sm.cam[1], x01.x, x01.y, x2v.x);
+        // G = 4 Jx_i Vd^-1 Jx_k^T, with all four 1/r^2 factors folded into one scale
+        const double mk00 = v00 * sk.aX[0] + v01 * sk.aX[1] + v02 * sk.aX[2];
+        const double mk01 = v01 * sk.aX[0] + v11 * sk.aX[1] + v12_ * sk.aX[2];
+        const double mk02 = v02 * sk.aX[0] + v12_ * sk.aX[1] + v22 * sk.aX[2];
+        const double mk10 = v00 * sk.bX[0] + v01 * sk.bX[1] + v02 * sk.bX[2];
+        const double mk11 = v01 * sk.bX[0] + v11 * sk.bX[1] + v12_ * sk.bX[2];
+        const double mk12 = v02 * sk.bX[0] + v12_ * sk.bX[1] + v22 * sk.bX[2];
+        const double rr = si.r * sk.r;
+        const double rr2 = rr * rr;
+        const double sc = 4.0 / (rr2 * rr2);
+        const double g00 = sc * (si.aX[0] * mk00 + si.aX[1] * mk01 + si.aX[2] * mk02);
+        const double g01 = sc * (si.aX[0] * mk10 + si.aX[1] * mk11 + si.aX[2] * mk12);
+        const double g10 = sc * (si.bX[0] * mk00 + si.bX[1] * mk01 + si.bX[2] * mk02);
+        const double g11 = sc * (si.bX[0] * mk10 + si.bX[1] * mk11 + si.bX[2] * mk12);
+        // rows of G Jc_k; Jc_k row a = [af, au, 0, -aX, aX x d], row b = [bf, 0, au, -bX, bX x d]
+        const double aw0 = sk.aX[1] * sk.d[2] - sk.aX[2] * sk.d[1];
+        const double aw1 = sk.aX[2] * sk.d[0] - sk.aX[0] * sk.d[2];
+        const double aw2 = sk.aX[0] * sk.d[1] - sk.aX[1] * sk.d[0];
+        const double bw0 = sk.bX[1] * sk.d[2] - sk.bX[2] * sk.d[1];
+        const double bw1 = sk.bX[2] * sk.d[0] - sk.bX[0] * sk.d[2];
+        const double bw2 = sk.bX[0] * sk.d[1] - sk.bX[1] * sk.d[0];
+        t0[0] = g00 * sk.af + g01 * sk.bf;  t1[0] = g10 * sk.af + g11 * sk.bf;
+        t0[1] = g00 * sk.au;                t1[1] = g10 * sk.au;
+        t0[2] = g01 * sk.au;                t1[2] = g11 * sk.au;
 #pragma unroll
-        for (int u = 0; u < 9; ++u) {
-          const double2 v = *reinterpret_cast<const double2*>(pk + 2 * u);
-          jk[2 * u] = v.x;
-          jk[2 * u + 1] = v.y;
+        for (int m = 0; m < 3; ++m) {
+          t0[3 + m] = -(g00 * sk.aX[m] + g01 * sk.bX[m]);
+          t1[3 + m] = -(g10 * sk.aX[m] + g11 * sk.bX[m]);
         }
-#pragma unroll
-        for (int b = 0; b < 9; ++b) {
-          t0[b] = g00 * jk[b] + g01 * jk[9 + b];
-          t1[b] = g10 * jk[b] + g11 * jk[9 + b];
-        }
+        t0[6] = g00 * aw0 + g01 * bw0;  t1[6] = g10 * aw0 + g11 * bw0;
+        t0[7] = g00 * aw1 + g01 * bw1;  t1[7] = g10 * aw1 + g11 * bw1;
+        t0[8] = g00 * aw2 + g01 * bw2;  t1[8] = g10 * aw2 + g11 * bw2;
       }
-      double ji[18];
+      double ia[9], ib[9];
+      ia[0] = si.af;  ib[0] = si.bf;
+      ia[1] = si.au;  ib[1] = 0.0;
+      ia[2] = 0.0;    ib[2] = si.au;
 #pragma unroll
-      for (int u = 0; u < 9; ++u) {
-        const double2 v = *reinterpret_cast<const double2*>(pi + 2 * u);
-        ji[2 * u] = v.x;
-        ji[2 * u + 1] = v.y;
+      for (int m = 0; m < 3; ++m) {
+        ia[3 + m] = -si.aX[m];
+        ib[3 + m] = -si.bX[m];
       }
+      ia[6] = si.aX[1] * si.d[2] - si.aX[2] * si.d[1];  ib[6] = si.bX[1] * si.d[2] - si.bX[2] * si.d[1];
+      ia[7] = si.aX[2] * si.d[0] - si.aX[0] * si.d[2];  ib[7] = si.bX[2] * si.d[0] - si.bX[0] * si.d[2];
+      ia[8] = si.aX[0] * si.d[1] - si.aX[1] * si.d[0];  ib[8] = si.bX[0] * si.d[1] - si.bX[1] * si.d[0];
+      // 16-byte pieces swizzled by (lane / 2) % 4: the lanes of a quarter-warp hit distinct banks
 #pragma unroll
-      for (int a = 0; a < 9; ++a)
+      for (int u = 0; u < 4; ++u) {
+        i0[u ^ sw] = make_double2(ia[2 * u], ia[2 * u + 1]);
+        i1[u ^ sw] = make_double2(ib[2 * u], ib[2 * u + 1]);
+        t0s[u ^ sw] = make_double2(t0[2 * u], t0[2 * u + 1]);
+        t1s[u ^ sw] = make_double2(t1[2 * u], t1[2 * u + 1]);
+      }
+      // row 8, column 8 and the corner of the block stay with the lane
 #pragma unroll
-        for (int b = 0; b < 9; ++b) acc[a][b] = fma(ji[a], t0[b], fma(ji[9 + a], t1[b], acc[a][b]));
+      for (int a = 0; a < 8; ++a) {
+        r8[a] = fma(ia[8], t0[a], fma(ib[8], t1[a], r8[a]));
+        c8[a] = fma(ia[a], t0[8], fma(ib[a], t1[8], c8[a]));
+      }
+      c88 = fma(ia[8], t0[8], fma(ib[8], t1[8], c88));
+    } else {
+      const double2 z = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) i0[u] = i1[u] = t0s[u] = t1s[u] = z;
+    }
+    __syncwarp();
+    // leading 8x8: C += A B with A[a][kappa] = Jc_i row (kappa & 1) of point kappa / 2, entry a,
+    // and B[kappa][b] likewise from G Jc_k; 16 steps of K = 4 (two points each)
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      // the two points of step u are rows 2u, 2u + 1: their swizzle is u % 4
+      const int o = frag_base + 16 * u + ((((fg >> 1) ^ (u & 3)) << 1) | (fg & 1));
+      const double fa = sm.ifrag[o];
+      const double fb = sm.tfrag[o];
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(c0), "+d"(c1)
+                   : "d"(fa), "d"(fb));
     }
   };
 
   // Issue the gather of the next round (queue[0, cnt)), move the rest of the queue down, then
   // compute the previous round.
   auto round = [&](int cnt) {
-    const uint32_t sa = s_addr + (uint32_t)(rounds & 1) * (64 * kYS * 8);
-    if (cnt == 32) {
+    const uint32_t sa = s_addr + (uint32_t)(rounds & 1) * (32 * kPS * 8);
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        uint2 en;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(en.x), "=r"(en.y) : "r"(q_addr + 16u * u));
-        if (g_on) {
-          cp_async16(sa + 2 * u * kYS * 8, Yi + (size_t)en.x * kYB);
-          cp_async16(sa + (32 + 2 * u) * kYS * 8, Yk + (size_t)en.y * kYB);
-        }
-      }
-    } else {
-      for (int u = 0; 2 * u < cnt; ++u) {
-        const uint2 en = sm.queue[2 * u + g_sub];
-        if (g_on && 2 * u + g_sub < cnt) {
-          cp_async16(sa + 2 * u * kYS * 8, Yi + (size_t)en.x * kYB);
-          cp_async16(sa + (32 + 2 * u) * kYS * 8, Yk + (size_t)en.y * kYB);
-        }
-      }
+    for (int u = 0; u < 6; ++u) {
+      const int p = lane + 32 * u;
+      const int row = (p * 171) >> 10;  // p / 6 for p < 192
+      const int piece = p - 6 * row;
+      int j;
+      asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(j) : "r"(q_addr + 4u * row));
+      if (row < cnt) cp_async16(sa + (row * kPS + 2 * piece) * 8, PT + (size_t)j * kPT + 2 * piece);
     }
     cp_commit();
     qn -= cnt;
     {
-      const uint2 up = sm.queue[32 + lane];
+      // queue[32 + x] -> queue[x]
+      int up[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) up[u] = sm.queue[32 * (u + 1) + lane];
       __syncwarp();
-      sm.queue[lane] = up;
+#pragma unroll
+      for (int u = 0; u < 3; ++u) sm.queue[32 * u + lane] = up[u];
     }
     if (rounds > 0) {
       cp_wait<1>();
@@ -232,17 +295,18 @@ schur_pairs_kernel(int M, int64_t Wp, const uint2* __restrict__ bitpre,
 
   // bitmap words are fetched one batch ahead
   uint4 wi = bi[0], wk = bk[0];
-  for (int64_t w0 = 0; w0 < Wp; w0 += 64) {
+  for (int64_t w0 = 0; w0 < Wp; w0 += 128) {
     const uint4 ci = wi, ck = wk;
-    if (w0 + 64 < Wp) {
-      wi = bi[(w0 + 64) >> 1];
-      wk = bk[(w0 + 64) >> 1];
+    if (w0 + 128 < Wp) {
+      wi = bi[(w0 + 128) >> 2];
+      wk = bk[(w0 + 128) >> 2];
     }
-    const uint64_t mi = ((uint64_t)ci.z << 32) | ci.x, mk = ((uint64_t)ck.z << 32) | ck.x;
-    uint64_t c = mi & mk;
-    while (__any_sync(0xffffffffu, c != 0ull)) {
+    uint64_t c0 = ((uint64_t)(ci.y & ck.y) << 32) | (ci.x & ck.x);
+    uint64_t c1 = ((uint64_t)(ci.w & ck.w) << 32) | (ci.z & ck.z);
+    const int jbase = (int)(w0 + 4 * lane) * 32;
+    while (__any_sync(0xffffffffu, (c0 | c1) != 0ull)) {
       // exclusive prefix of the hit counts -> queue slots; hits that do not fit wait for the next pass
-      const int n = __popcll(c);
+      const int n = __popcll(c0) + __popcll(c1);
       int incl = n;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
@@ -251,13 +315,17 @@ schur_pairs_kernel(int M, int64_t Wp, const uint2* __restrict__ bitpre,
       }
       const int total = __shfl_sync(0xffffffffu, incl, 31);
       int pos = qn + incl - n;
-      while (c != 0ull && pos < 64) {
-        const int b = __ffsll((long long)c) - 1;
-        c &= c - 1;
-        const uint64_t below = (1ull << b) - 1ull;
-        sm.queue[pos++] = make_uint2(ci.y + __popcll(mi & below), ck.y + __popcll(mk & below));
+      while (c0 != 0ull && pos < kQueue) {
+        const int b = __ffsll((long long)c0) - 1;
+        c0 &= c0 - 1;
+        sm.queue[pos++] = jbase + b;
       }
-      qn = qn + total < 64 ? qn + total : 64;
+      while (c0 == 0ull && c1 != 0ull && pos < kQueue) {
+        const int b = __ffsll((long long)c1) - 1;
+        c1 &= c1 - 1;
+        sm.queue[pos++] = jbase + 64 + b;
+      }
+      qn = qn + total < kQueue ? qn + total : kQueue;
       __syncwarp();
       while (qn >= 32) round(32);
     }
@@ -269,23 +337,42 @@ schur_pairs_kernel(int M, int64_t Wp, const uint2* __restrict__ bitpre,
     compute((rounds - 1) & 1, cnt_prev);
   }
 
-  // fixed-order butterfly over the 32 lanes, then lane e % 32 stores entry e
+  // leading 8x8 straight from the C fragments; row 8, column 8 and the corner after a fixed-order
+  // butterfly over the 32 lanes.  Rows / columns of gauge-pinned parameters (:62-72) are zero.
+  const uint32_t mask_i = gauge_mask(i, axis), mask_k = gauge_mask(k, axis);
+  {
+    double* dst = P + (size_t)(9 * i + fg) * ld + 9 * k + 2 * fkq;
+    const bool pin_r = (mask_i >> fg) & 1u;
+    dst[0] = (pin_r || ((mask_k >> (2 * fkq)) & 1u)) ? 0.0 : c0;
+    dst[1] = (pin_r || ((mask_k >> (2 * fkq + 1)) & 1u)) ? 0.0 : c1;
+  }
 #pragma unroll
-  for (int a = 0; a < 9; ++a)
+  for (int a = 0; a < 8; ++a) {
+    double v = r8[a], w = c8[a];
 #pragma unroll
-    for (int b = 0; b < 9; ++b) {
-      double v = acc[a][b];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      if (lane == ((a * 9 + b) & 31)) P[(size_t)(9 * i + a) * ld + 9 * k + b] = v;
+    for (int off = 16; off > 0; off >>= 1) {
+      v += __shfl_xor_sync(0xffffffffu, v, off);
+      w += __shfl_xor_sync(0xffffffffu, w, off);
     }
+    if (((mask_i >> 8) | (mask_k >> a)) & 1u) v = 0.0;
+    if (((mask_i >> a) | (mask_k >> 8)) & 1u) w = 0.0;
+    if (lane == a) P[(size_t)(9 * i + 8) * ld + 9 * k + a] = v;
+    if (lane == 8 + a) P[(size_t)(9 * i + a) * ld + 9 * k + 8] = w;
+  }
+  {
+    double v = c88;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (((mask_i >> 8) | (mask_k >> 8)) & 1u) v = 0.0;
+    if (lane == 16) P[(size_t)(9 * i + 8) * ld + 9 * k + 8] = v;
+  }
 }
 
 // ---- diagonal blocks and rhs --------------------------------------------------------------------
-// grid (chunks, M): block (c, i) reduces chunk c of camera i's slice into 54 numbers.
+// grid (chunks, M): block (c, i) reduces chunk c of camera i's observations into 54 numbers.
 __global__ void __launch_bounds__(128)
 schur_diag_kernel(const int64_t* __restrict__ cam_ptr, const int32_t* __restrict__ cm_perm,
-                  const int32_t* __restrict__ obs_pt, const double* __restrict__ Ycm,
+                  const int32_t* __restrict__ obs_pt, const double* __restrict__ Ysp,
                   const double* __restrict__ Z, double* __restrict__ Dpart, const ba_lm_state* ctl) {
   if (ctl && ctl->done) return;
   const int i = blockIdx.y;
@@ -298,35 +385,20 @@ schur_diag_kernel(const int64_t* __restrict__ cam_ptr, const int32_t* __restrict
 #pragma unroll
   for (int q = 0; q < kDiagPart; ++q) acc[q] = 0.0;
   for (int64_t q = lo + threadIdx.x; q < hi; q += blockDim.x) {
-    const double2* row = reinterpret_cast<const double2*>(Ycm + (size_t)(seg_lo + q) * kYB);
-    double v[kYB];
+    const int o = cm_perm[seg_lo + q];
+    const double* y = Ysp + (size_t)o * 27;  // [d][a]
+    const double* z = Z + 3 * (size_t)obs_pt[o];
+    double v[27];
 #pragma unroll
-    for (int u = 0; u < kYB / 2; ++u) {
-      const double2 t2 = row[u];
-      v[2 * u] = t2.x;
-      v[2 * u + 1] = t2.y;
-    }
-    const double* z = Z + 3 * (size_t)obs_pt[cm_perm[seg_lo + q]];
+    for (int u = 0; u < 27; ++u) v[u] = y[u];
     const double z0 = z[0], z1 = z[1], z2 = z[2];
-    const double* ja = v;
-    const double* jb = v + 9;
-    const double* ta = v + 18;
-    const double* tb = v + 21;
-    const double gaa = ta[0] * ta[0] + ta[1] * ta[1] + ta[2] * ta[2];
-    const double gab = ta[0] * tb[0] + ta[1] * tb[1] + ta[2] * tb[2];
-    const double gbb = tb[0] * tb[0] + tb[1] * tb[1] + tb[2] * tb[2];
-    const double za = ta[0] * z0 + ta[1] * z1 + ta[2] * z2;
-    const double zb = tb[0] * z0 + tb[1] * z1 + tb[2] * z2;
     int idx = 0;
 #pragma unroll
-    for (int r = 0; r < 9; ++r) {
-      const double t0 = gaa * ja[r] + gab * jb[r];
-      const double t1 = gab * ja[r] + gbb * jb[r];
+    for (int r = 0; r < 9; ++r)
 #pragma unroll
-      for (int c = r; c < 9; ++c) acc[idx++] += t0 * ja[c] + t1 * jb[c];
-    }
+      for (int c = r; c < 9; ++c) acc[idx++] += v[r] * v[c] + v[9 + r] * v[9 + c] + v[18 + r] * v[18 + c];
 #pragma unroll
-    for (int r = 0; r < 9; ++r) acc[45 + r] += ja[r] * za + jb[r] * zb;
+    for (int r = 0; r < 9; ++r) acc[45 + r] += v[r] * z0 + v[9 + r] * z1 + v[18 + r] * z2;
   }
   __shared__ double sred[4][kDiagPart];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -371,7 +443,7 @@ __global__ void schur_diag_finish_kernel(int nchunks, const double* __restrict__
 int launch_schur_sparse(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
   ProfScope ps(e, PG_SYRK, s);
   dim3 dgrid(e->cam_chunks, e->M);
-  schur_diag_kernel<<<dgrid, 128, 0, s>>>(e->cam_ptr, e->cm_perm, e->obs_pt, e->Ycm, e->Z, e->Upart, ctl);
+  schur_diag_kernel<<<dgrid, 128, 0, s>>>(e->cam_ptr, e->cm_perm, e->obs_pt, e->Ysp, e->Z, e->Upart, ctl);
   BA_LAUNCH_CHECK();
   schur_diag_finish_kernel<<<e->M, 96, 0, s>>>(e->cam_chunks, e->Upart, e->P(), e->n_pad, e->rhs_row, ctl);
   BA_LAUNCH_CHECK();
@@ -383,8 +455,8 @@ int launch_schur_sparse(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
   }
   BA_CUDA(cudaFuncSetAttribute(schur_pairs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                (int)cudaSharedmemCarveoutMaxShared));
-  schur_pairs_kernel<<<(unsigned)n_items, 32, 0, s>>>(e->M, e->Wp, e->bitpre, e->cam_ptr, e->Ycm, e->P(),
-                                                     e->n_pad, ctl);
+  schur_pairs_kernel<<<(unsigned)n_items, 32, 0, s>>>(e->M, e->axis, e->Wp, e->bits, e->camtab[0], e->f0,
+                                                     e->PT, e->P(), e->n_pad, ctl);
   BA_LAUNCH_CHECK();
   return BA_OK;
 }
