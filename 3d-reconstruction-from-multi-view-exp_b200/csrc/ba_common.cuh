@@ -123,7 +123,14 @@ struct ba_engine {
 
   ba_lm_state* ctl = nullptr;       // device
   ba_iter_record* rec = nullptr;    // device [kMaxRecords]
-  ba_lm_state* ctl_host = nullptr;  // pinned
+  ba_lm_state* ctl_host = nullptr;  // pinned [4]: [0] read_ctl, [1], [2] the two solve graphs
+
+  // the LM loop as CUDA graphs (ba_lm_run): one inner solve per graph, two instances (A/B) so
+  // that each has its own pinned control-block slot and completion event
+  cudaStream_t own_stream = nullptr;
+  cudaGraphExec_t solve_graph[2] = {nullptr, nullptr};
+  cudaEvent_t solve_ev[2] = {nullptr, nullptr};
+  int64_t graph_launches = 0;  // kernels per graph
 
   // profiling
   bool profiling = false;

@@ -3,8 +3,11 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <chrono>
+#include <mutex>
 #include <vector>
 
 #include "ba_common.cuh"
@@ -44,6 +47,31 @@ static int retain_pool_memory(int device) {
   uint64_t keep = UINT64_MAX;
   BA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   return BA_OK;
+}
+
+// Pinned control blocks (4 ba_lm_state each) are recycled for the life of the process:
+// cudaMallocHost / cudaFreeHost synchronise the device and take 15+ ms, which is more than a whole
+// C2 adjustment, so an engine must not pay them.
+static std::mutex g_pin_mutex;
+static std::vector<ba_lm_state*> g_pin_free;
+
+static ba_lm_state* pinned_block_acquire() {
+  std::lock_guard<std::mutex> lock(g_pin_mutex);
+  if (g_pin_free.empty()) {
+    constexpr int kSlab = 8;
+    ba_lm_state* slab = nullptr;
+    if (cudaMallocHost(reinterpret_cast<void**>(&slab), kSlab * 4 * sizeof(ba_lm_state)) != cudaSuccess) return nullptr;
+    for (int k = 0; k < kSlab; ++k) g_pin_free.push_back(slab + 4 * k);
+  }
+  ba_lm_state* p = g_pin_free.back();
+  g_pin_free.pop_back();
+  return p;
+}
+
+static void pinned_block_release(ba_lm_state* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_pin_mutex);
+  g_pin_free.push_back(p);
 }
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -129,7 +157,15 @@ static void free_engine(ba_engine* e) {
                   e->dxi, e->cost_part, e->cost_buf, e->ctl, e->rec};
   for (void* p : ptrs)
     dev_free(p);
-  if (e->ctl_host) cudaFreeHost(e->ctl_host);
+  for (int k = 0; k < 2; ++k) {
+    if (e->solve_graph[k]) cudaGraphExecDestroy(e->solve_graph[k]);
+    if (e->solve_ev[k]) cudaEventDestroy(e->solve_ev[k]);
+  }
+  if (e->own_stream) {
+    cudaStreamSynchronize(e->own_stream);  // nothing may still be copying into the pinned block
+    cudaStreamDestroy(e->own_stream);
+  }
+  pinned_block_release(e->ctl_host);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   delete e;
@@ -145,7 +181,19 @@ static int alloc_cam(CamState* c, int M) {
   return BA_OK;
 }
 
+struct StepTimer {
+  bool on = std::getenv("BA_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[ba timing] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 static int create_engine(const ba_problem* p, ba_engine** out) {
+  StepTimer tm;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_error("no CUDA device: this engine has no CPU path");
@@ -169,20 +217,25 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
     return BA_ERR_INVALID;
   }
   BA_CUDA(cudaSetDevice(p->device));
+  tm.lap("device count / set device");
   BA_TRY(retain_pool_memory(p->device));
+  tm.lap("pool attribute");
   ba_engine* e = new (std::nothrow) ba_engine();
   if (!e) { set_error("out of host memory"); return BA_ERR_CUDA; }
   e->prob = *p;
   e->N = p->n_points; e->nobs = p->n_obs; e->M = p->n_cams; e->dense = p->dense ? 1 : 0;
   e->axis = p->axis; e->device = p->device; e->f0 = p->f0;
-  cudaDeviceProp prop;
-  BA_CUDA(cudaGetDeviceProperties(&prop, p->device));
-  e->num_sms = prop.multiProcessorCount;
+  BA_CUDA(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, p->device));
+  tm.lap("device attribute");
 
   e->n_full = 9 * e->M;
   e->rhs_row = e->n_full;
   const int n_aug = e->n_full + 1;
   e->syrk_tile = n_aug <= 1024 ? 64 : 128;
+  if (const char* t = std::getenv("BA_SYRK_TILE")) {  // tuning experiments only
+    const int v = std::atoi(t);
+    if (v == 64 || v == 128) e->syrk_tile = v;
+  }
   e->n_pad = round_up(n_aug, 8);  // fragment granularity; edge tiles of the SYRK are partial
   e->k_pad = round_up64(3 * e->N, 32);
   e->syrk_splits = syrk_choose_splits(e->n_pad, e->syrk_tile, e->k_pad, e->num_sms);
@@ -242,10 +295,12 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
   A(dev_alloc(&e->ctl, (size_t)1));
   A(dev_alloc(&e->rec, (size_t)kMaxRecords));
 #undef A
-  if (st == BA_OK && cudaMallocHost(reinterpret_cast<void**>(&e->ctl_host), sizeof(ba_lm_state)) != cudaSuccess) {
+  tm.lap("device allocations");
+  if (st == BA_OK && !(e->ctl_host = pinned_block_acquire())) {
     set_error("cudaMallocHost failed");
     st = BA_ERR_CUDA;
   }
+  tm.lap("pinned control block");
   if (st == BA_OK) {
     cudaEventCreate(&e->ev0);
     cudaEventCreate(&e->ev1);
@@ -259,6 +314,7 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
       st = BA_ERR_CUDA;
     }
   }
+  tm.lap("events, memsets, sync");
   if (st != BA_OK) {
     free_engine(e);
     return st;
@@ -501,18 +557,85 @@ int ba_lm_records(ba_engine* e, ba_iter_record* records, int max_records, int* n
   return BA_OK;
 }
 
+// One inner solve (linearise if needed, reduce, factor, solve, trial, decide) captured as a CUDA
+// graph.  Every kernel of the sequence takes its decisions from the device-resident control
+// block, so the same graph serves every solve; it ends with the copy of the control block into
+// pinned slot `slot`.
+static int capture_solve_graph(ba_engine* e, int slot) {
+  cudaStream_t s = e->own_stream;
+  const int64_t before = g_launch_count;
+  cudaGraph_t graph = nullptr;
+  BA_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int st = phase_reduce(e, true, 0.0, s);
+  if (st == BA_OK) st = phase_solve(e, true, 0.0, s);
+  if (st == BA_OK) st = launch_decide(e, s);
+  if (st == BA_OK &&
+      cudaMemcpyAsync(e->ctl_host + 1 + slot, e->ctl, sizeof(ba_lm_state), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    st = BA_ERR_CUDA;
+  const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+  e->graph_launches = g_launch_count - before;
+  g_launch_count = before;  // nothing ran yet; every graph launch adds graph_launches
+  if (st != BA_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    if (st == BA_OK) set_error("graph capture failed: %s", cudaGetErrorString(ce));
+    cudaGetLastError();
+    return st != BA_OK ? st : BA_ERR_CUDA;
+  }
+  const cudaError_t ie = cudaGraphInstantiate(&e->solve_graph[slot], graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+    return BA_ERR_CUDA;
+  }
+  if (!e->solve_ev[slot]) BA_CUDA(cudaEventCreateWithFlags(&e->solve_ev[slot], cudaEventDisableTiming));
+  return BA_OK;
+}
+
+// The whole LM loop.  Without profiling the solves run as CUDA graphs on the engine's own stream,
+// one solve ahead of the host: graph n+1 is launched before the control block of solve n is read,
+// so the device never waits for the host (after termination the extra graph is a chain of
+// early-exit kernels).  With profiling on (per-phase event timing) the launches stay eager.
 int ba_lm_run(ba_engine* e, double scale_factor, double delta_tol, int max_iter, int max_retries,
               ba_iter_record* records, int max_records, int* n_records, ba_lm_state* final_state,
               void* stream) {
-  BA_TRY(ba_lm_begin(e, scale_factor, delta_tol, max_iter, max_retries, stream));
-  cudaStream_t s = (cudaStream_t)stream;
+  BA_TRY(check_ready(e));
+  cudaStream_t user = (cudaStream_t)stream;
   ba_lm_state st;
   std::memset(&st, 0, sizeof(st));
-  while (!st.done) {
-    BA_TRY(phase_reduce(e, true, 0.0, s));
-    BA_TRY(phase_solve(e, true, 0.0, s));
-    { ProfScope ps(e, PG_OTHER, s); BA_TRY(launch_decide(e, s)); }
-    BA_TRY(read_ctl(e, &st, s));
+  if (e->profiling || std::getenv("BA_NO_GRAPH")) {
+    BA_TRY(ba_lm_begin(e, scale_factor, delta_tol, max_iter, max_retries, stream));
+    while (!st.done) {
+      BA_TRY(phase_reduce(e, true, 0.0, user));
+      BA_TRY(phase_solve(e, true, 0.0, user));
+      { ProfScope ps(e, PG_OTHER, user); BA_TRY(launch_decide(e, user)); }
+      BA_TRY(read_ctl(e, &st, user));
+    }
+  } else {
+    if (!e->own_stream) BA_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    cudaStream_t s = e->own_stream;
+    // order after whatever the caller queued on its stream
+    BA_CUDA(cudaEventRecord(e->ev0, user));
+    BA_CUDA(cudaStreamWaitEvent(s, e->ev0, 0));
+    BA_TRY(ba_lm_begin(e, scale_factor, delta_tol, max_iter, max_retries, s));
+    for (int k = 0; k < 2; ++k)
+      if (!e->solve_graph[k]) BA_TRY(capture_solve_graph(e, k));
+    int n = 0;  // graphs launched
+    BA_CUDA(cudaGraphLaunch(e->solve_graph[0], s));
+    BA_CUDA(cudaEventRecord(e->solve_ev[0], s));
+    g_launch_count += e->graph_launches;
+    n = 1;
+    while (true) {
+      // speculative: the next solve is queued before this one's decision is known
+      const int nxt = n & 1;
+      BA_CUDA(cudaGraphLaunch(e->solve_graph[nxt], s));
+      BA_CUDA(cudaEventRecord(e->solve_ev[nxt], s));
+      g_launch_count += e->graph_launches;
+      ++n;
+      BA_CUDA(cudaEventSynchronize(e->solve_ev[nxt ^ 1]));
+      st = e->ctl_host[1 + (nxt ^ 1)];
+      if (st.done) break;
+    }
+    BA_CUDA(cudaStreamSynchronize(s));  // the speculative tail (no-ops) must not outlive the call
   }
   if (final_state) *final_state = st;
   if (n_records) BA_TRY(ba_lm_records(e, records, max_records, n_records, stream));

@@ -31,7 +31,8 @@ __device__ __forceinline__ double rcp_newton(double d) {
   return r;
 }
 
-constexpr int kPanelThreads = 2 * NB;  // one thread per row of the tall panel
+constexpr int kPanelThreads = 8 * NB;  // 4 threads per row of the tall panel (16 columns each)
+constexpr int kPanelCols = 16;          // columns per thread
 
 __global__ void __launch_bounds__(kPanelThreads)
 chol_panel_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb,
@@ -40,85 +41,83 @@ chol_panel_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb,
   extern __shared__ double psm[];
   // tall panel T[128][65]: rows 0..63 the diagonal block, rows 64..127 this block's rows
   double(*T)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(psm);
-  double* col = psm + 2 * NB * (NB + 1);  // [2][128] published pivot column (double buffered;
-                                          // entries 64..127 stay zero: shifted-out window columns)
+  double* col = psm + 2 * NB * (NB + 1);  // [2][128] published pivot column (double buffered)
   double* piv = col + 4 * NB;             // [64] pivots d_k
   __shared__ int s_fail;
   const int tid = threadIdx.x;
   // block 0 carries the rows of the identity (-> W = L_D^-T), block b >= 1 the 64 rows from rbase
   const int rbase = k0 + nb + ((int)blockIdx.x - 1) * NB;
   if (tid == 0) s_fail = 0;
-  for (int q = tid; q < 4 * NB; q += kPanelThreads) col[q] = 0.0;
   {
     // coalesced loads, all issued before the first use (L2 latency paid once)
-    double vd[32], va[32];
+    double vd[8], va[8];
     const int c = tid & 63;
 #pragma unroll
-    for (int u = 0; u < 32; ++u) {
-      const int r = (tid >> 6) + 2 * u;
+    for (int u = 0; u < 8; ++u) {
+      const int r = (tid >> 6) + 8 * u;
       vd[u] = (r == c) ? 1.0 : 0.0;
       if (r < nb && c <= r) vd[u] = S[(size_t)(k0 + r) * ld + k0 + c];
       va[u] = (blockIdx.x == 0 && r == c) ? 1.0 : 0.0;
       if (blockIdx.x != 0 && rbase + r < n_rows && c < nb) va[u] = S[(size_t)(rbase + r) * ld + k0 + c];
     }
 #pragma unroll
-    for (int u = 0; u < 32; ++u) {
-      const int r = (tid >> 6) + 2 * u;
+    for (int u = 0; u < 8; ++u) {
+      const int r = (tid >> 6) + 8 * u;
       T[r][c] = vd[u];
       T[NB + r][c] = va[u];
     }
   }
   __syncthreads();
-  // Each thread keeps one row of the tall panel in registers.  Right-looking elimination with
-  // unscaled columns (A = Lu D^-1 Lu^T):  a[r][c] -= a[r][k] a[c][k] / d_k  for c > k (diagonal
-  // block: c <= r).  The rows below the diagonal block ride along, so there is no separate
-  // triangular solve.  Per column: the diagonal-block rows publish their column-k entry, one
-  // barrier, then every row does broadcast loads + FMAs from registers.  Columns are processed
-  // in groups of 8 with the register window shifted after each group, so the (unrolled) body is
-  // 8 columns long and stays in the instruction cache.
-  const int r = tid;         // row of the tall panel
-  const bool drow = r < NB;  // diagonal-block row
-  double a[NB];              // window: a[j] <-> column kb + j
+  // Right-looking elimination with unscaled columns (A = Lu D^-1 Lu^T):
+  //   a[r][c] -= a[r][k] a[c][k] / d_k   for c > k  (diagonal block: c <= r matters).
+  // The rows below the diagonal block ride along, so there is no separate triangular solve.
+  // Thread (r, cg) keeps columns 16 cg .. 16 cg + 15 of row r in registers; warps are uniform in
+  // cg.  Per column: the owners publish column k of all 128 rows, one barrier, then every thread
+  // still holding live columns does <= 16 FMAs with broadcast loads of the pivot row.  The whole
+  // column step is one dependent chain (publish -> barrier -> reciprocal -> scale -> FMA ->
+  // publish), so the 4-way split of a row is what shortens the panel: 16 instead of 64 FMAs behind
+  // every barrier, 16 warps instead of 4 to hide the FP64 and shared-memory latencies.
+  const int r = tid & (2 * NB - 1);  // row of the tall panel
+  const int cg = tid >> 7;           // column group
+  double a[kPanelCols];
 #pragma unroll
-  for (int c = 0; c < NB; ++c) a[c] = T[r][c];
-  for (int kb = 0; kb < NB; kb += 8) {
-    const int live = (NB - kb) >> 3;  // column groups of the window still inside the panel
+  for (int j = 0; j < kPanelCols; ++j) a[j] = T[r][kPanelCols * cg + j];
+  for (int g = 0; g < NB / kPanelCols; ++g) {
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-      const int k = kb + kk;
+    for (int kk = 0; kk < kPanelCols; ++kk) {
+      const int k = kPanelCols * g + kk;
       double* ck = col + (kk & 1) * (2 * NB);
-      if (drow && r >= k) ck[r] = a[kk];
+      if (cg == g) ck[r] = a[kk];
       __syncthreads();
-      const double d = ck[k];
-      if (r == k) piv[k] = d;
-      const double invd = rcp_newton(d);
-      const double la = a[kk] * invd;
-      // No per-element predicates: rows r <= k and the upper triangle of the diagonal block
-      // accumulate values nobody reads (only entries with column <= row are published/stored).
-      const double2* ck2 = reinterpret_cast<const double2*>(ck + kb);
+      if (cg >= g) {  // warp-uniform; groups < g hold finished columns only
+        const double d = ck[k];
+        if (r == k && cg == g) piv[k] = d;
+        const double la = ck[r] * rcp_newton(d);
+        const double2* pr = reinterpret_cast<const double2*>(ck + kPanelCols * cg);
+        if (cg > g) {
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        if (g < live) {  // block-uniform
+          for (int jp = 0; jp < kPanelCols / 2; ++jp) {
+            const double2 cv = pr[jp];
+            a[2 * jp] = fma(-la, cv.x, a[2 * jp]);
+            a[2 * jp + 1] = fma(-la, cv.y, a[2 * jp + 1]);
+          }
+        } else {
+          // No per-row predicates: rows r <= k and the upper triangle of the diagonal block
+          // accumulate values nobody reads.
 #pragma unroll
-          for (int jp = 0; jp < 4; ++jp) {
-            const int j = 8 * g + 2 * jp;
-            if (j + 1 > kk) {
-              const double2 cv = ck2[j >> 1];
-              if (j > kk) a[j] = fma(-la, cv.x, a[j]);
-              a[j + 1] = fma(-la, cv.y, a[j + 1]);
+          for (int jp = 0; jp < kPanelCols / 2; ++jp) {
+            if (2 * jp + 1 > kk) {
+              const double2 cv = pr[jp];
+              if (2 * jp > kk) a[2 * jp] = fma(-la, cv.x, a[2 * jp]);
+              a[2 * jp + 1] = fma(-la, cv.y, a[2 * jp + 1]);
             }
           }
         }
       }
     }
-    // the 8 finished (unscaled) columns go back to the tile; shift the window
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) T[r][kb + kk] = a[kk];
-#pragma unroll
-    for (int j = 0; j < NB - 8; ++j) a[j] = a[j + 8];
-#pragma unroll
-    for (int j = NB - 8; j < NB; ++j) a[j] = 0.0;
   }
+#pragma unroll
+  for (int j = 0; j < kPanelCols; ++j) T[r][kPanelCols * cg + j] = a[j];
   __syncthreads();
   if (tid < NB) {
     const double d = piv[tid];

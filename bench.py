@@ -42,6 +42,7 @@ SCALE, TOL_NEVER = 2.0, -1.0  # optimize(2.0, ...) as in the reference script; t
 
 # bounded CPU samples (points of the named scene, cameras unchanged, LM iterations)
 CPU_SAMPLE = {"c2": (10_000, 2), "c3": (1_500, 1), "c4": (250, 1), "c5": (250, 1)}
+E2E_REPS = 3
 REF_STEP_SAMPLE = {"c2": 2_000, "c3": 800, "c4": 150, "c5": 150}
 
 
@@ -300,7 +301,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
             avg_ms = k3["ms"] / max(adj.engine.lm_state().solves, 1)
             achieved = flops / (avg_ms * 1e-3) / 1e12
             out["roofline"] = {
-                "kernel": "schur_sparse_atomic_kernel (K3, sparse Schur products)",
+                "kernel": "schur_pairs_kernel + schur_diag_kernel (K3, sparse Schur products, matrix-free pair kernel)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": None, "algorithmic_flops_per_launch": flops,
                 "avg_launch_ms": avg_ms, "share_of_step": k3["ms"] / tot if tot > 0 else None,
@@ -324,28 +325,34 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     # caller that adjusts scene after scene would
     adj.engine.close()
     # ---- end-to-end arm (host buffers in, host results out) ---------------------------------
-    barrier()
-    t0 = time.perf_counter()
-    adj2 = make_adjuster()
-    with contextlib.redirect_stdout(io.StringIO()):
-        Xr, Kr, Rr, tr = adj2.optimize(SCALE, TOL_NEVER, max_iter=K)
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
-    assert len(adj2.records) == K
+    # Each repetition is the complete user call for K steps; the median of E2E_REPS wall times is
+    # reported (all samples are listed), since a single cold call is dominated by allocator noise.
     state_bytes = (3 * sc.n_points + 15 * sc.n_cams) * 8
     h2d = h_xy.nbytes + h_ptr.nbytes + (0 if h_cam is None else h_cam.nbytes) + state_bytes
     d2h = state_bytes + K * 40 + (st.solves + 1) * 88
-    adj2.engine.close()
+    e2e_samples = []
+    for _ in range(E2E_REPS):
+        barrier()
+        t0 = time.perf_counter()
+        adj2 = make_adjuster()
+        with contextlib.redirect_stdout(io.StringIO()):
+            Xr, Kr, Rr, tr = adj2.optimize(SCALE, TOL_NEVER, max_iter=K)
+        torch.cuda.synchronize()
+        e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        e2e_samples.append(float(e2e_t.item()))
+        assert len(adj2.records) == K
+        adj2.engine.close()
+    e2e_s = float(np.median(e2e_samples))
 
     if rank == 0:
         out["e2e"] = {"value": nobs_total * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / K,
                       "d2h_bytes_per_step": d2h / K, "ms_per_step": e2e_s / K * 1e3,
+                      "samples_ms_per_step": [t / K * 1e3 for t in e2e_samples],
                       "what": "BundleAdjuster.from_observations(pinned host arrays).optimize(max_iter=K): "
                               "engine creation (device memory from the library's retained pool), H2D, "
-                              "K iterations, D2H of X/K/R/t"}
+                              f"K iterations, D2H of X/K/R/t; median of {E2E_REPS} such calls"}
 
     if rank == 0:
         out["clocks"] = sampler.stop(t_wall0, t_wall1)
