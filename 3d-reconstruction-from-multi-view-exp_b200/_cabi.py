@@ -63,6 +63,8 @@ SIGNATURES = {
     "ba_lm_phase_solve": (C.c_int, [_P, _P]),
     "ba_lm_phase_decide": (C.c_int, [_P, _P]),
     "ba_lm_state_get": (C.c_int, [_P, C.POINTER(LMState), _P]),
+    "ba_lm_state_post": (C.c_int, [_P, C.c_int, _P]),
+    "ba_lm_state_wait": (C.c_int, [_P, C.c_int, C.POINTER(LMState)]),
     "ba_lm_iterate": (C.c_int, [_P, C.POINTER(LMState), _P]),
     "ba_lm_run": (C.c_int, [_P, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(IterRecord),
                             C.c_int, C.POINTER(C.c_int), C.POINTER(LMState), _P]),

@@ -525,6 +525,23 @@ int ba_lm_state_get(ba_engine* e, ba_lm_state* out, void* stream) {
   return read_ctl(e, out, (cudaStream_t)stream);
 }
 
+int ba_lm_state_post(ba_engine* e, int slot, void* stream) {
+  if (!e || (slot != 0 && slot != 1)) { set_error("bad argument"); return BA_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  BA_CUDA(cudaSetDevice(e->device));
+  if (!e->solve_ev[slot]) BA_CUDA(cudaEventCreateWithFlags(&e->solve_ev[slot], cudaEventDisableTiming));
+  BA_CUDA(cudaMemcpyAsync(e->ctl_host + 1 + slot, e->ctl, sizeof(ba_lm_state), cudaMemcpyDeviceToHost, s));
+  BA_CUDA(cudaEventRecord(e->solve_ev[slot], s));
+  return BA_OK;
+}
+
+int ba_lm_state_wait(ba_engine* e, int slot, ba_lm_state* out) {
+  if (!e || !out || (slot != 0 && slot != 1) || !e->solve_ev[slot]) { set_error("bad argument"); return BA_ERR_INVALID; }
+  BA_CUDA(cudaEventSynchronize(e->solve_ev[slot]));
+  *out = e->ctl_host[1 + slot];
+  return BA_OK;
+}
+
 int ba_lm_iterate(ba_engine* e, ba_lm_state* out, void* stream) {
   BA_TRY(check_ready(e));
   cudaStream_t s = (cudaStream_t)stream;

@@ -148,6 +148,16 @@ class Engine:
         _cabi.check(self._lib.ba_lm_state_get(self._h, C.byref(st), self.stream))
         return st
 
+    def lm_state_post(self, slot: int) -> None:
+        """Enqueue a copy of the control block into pinned slot 0/1 (no host synchronisation)."""
+        _cabi.check(self._lib.ba_lm_state_post(self._h, int(slot), self.stream))
+
+    def lm_state_wait(self, slot: int) -> _cabi.LMState:
+        """Block until the copy posted into `slot` has landed and return it."""
+        st = _cabi.LMState()
+        _cabi.check(self._lib.ba_lm_state_wait(self._h, int(slot), C.byref(st)))
+        return st
+
     def lm_iterate(self) -> _cabi.LMState:
         st = _cabi.LMState()
         _cabi.check(self._lib.ba_lm_iterate(self._h, C.byref(st), self.stream))

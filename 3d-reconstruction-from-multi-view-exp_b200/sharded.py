@@ -47,16 +47,42 @@ def lm_loop(engine, dist, group, scale_factor, delta_tol, max_iter, max_retries=
     cost = engine.cost_tensor()
     engine.lm_begin(scale_factor, delta_tol, max_iter, max_retries)
     dist.all_reduce(cost[0:1], group=group)  # cost of the initial state (:85-87)
-    while True:
+
+    def enqueue_solve():
         engine.lm_phase_reduce()
         dist.all_reduce(red, group=group)
         engine.lm_phase_solve()
         dist.all_reduce(cost[1:2], group=group)
         engine.lm_phase_decide()
+
+    if on_state is None and hasattr(engine, "lm_state_post"):
+        # One solve ahead of the host: solve n+1 is queued (kernels and both all-reduces) before
+        # the control block of solve n is read, so the device never idles while the host
+        # launches.  After termination every kernel of the extra solve is a no-op and the extra
+        # all-reduces sum buffers that nobody reads again; `done` is identical on all ranks (it
+        # derives from all-reduced data), so all ranks issue the same collectives.
+        enqueue_solve()
+        engine.lm_state_post(0)
+        n = 1
+        while True:
+            enqueue_solve()
+            engine.lm_state_post(n & 1)
+            st = engine.lm_state_wait((n & 1) ^ 1)
+            n += 1
+            if st.done:
+                engine.lm_state_wait((n & 1) ^ 1)  # drain the speculative solve
+                return st
+    while True:
+        enqueue_solve()
         st = engine.lm_state()
         if on_state is not None:
             on_state(st)
         if st.done:
+            if hasattr(engine, "lm_state_post"):
+                # ranks may mix this loop with the one above (e.g. is_debug on rank 0 only): issue
+                # the same trailing pair of (no-op) collectives so the sequences match
+                enqueue_solve()
+                engine.lm_state()
             return st
 
 
@@ -91,8 +117,19 @@ def run_sharded(adjuster, scale_factor, delta_tol, max_iter, is_debug):
         # the initial cost needs the all-reduce that lm_loop performs; log the state now and
         # patch the cost in afterwards
         adjuster._log_state(float("nan"))
-    st = lm_loop(eng, dist, adjuster._group, scale_factor, delta_tol, max_iter,
-                 adjuster._max_retries, on_state)
+        st = lm_loop(eng, dist, adjuster._group, scale_factor, delta_tol, max_iter,
+                     adjuster._max_retries, on_state)
+    else:
+        # no per-iteration host work: the loop runs one solve ahead of the host and the
+        # iteration lines are printed afterwards (same text, as in the single-GPU path)
+        st = lm_loop(eng, dist, adjuster._group, scale_factor, delta_tol, max_iter,
+                     adjuster._max_retries, None)
+        for rec in eng.lm_records():
+            if rank == 0:
+                adjuster._record(rec.E_prev, rec.E, rec.delta, rec.c, rec.solves, rec.count)
+            else:
+                adjuster.records.append({"E_prev": rec.E_prev, "E": rec.E, "delta": rec.delta,
+                                         "c": rec.c, "solves": rec.solves, "count": rec.count})
     if is_debug and adjuster.records:
         adjuster._log[0]["reprojection_error"] = np.float64(adjuster.records[0]["E_prev"])
     if st.status == _cabi.BA_ERR_SINGULAR:

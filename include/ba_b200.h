@@ -139,6 +139,12 @@ int ba_lm_phase_solve(ba_engine* e, void* stream);
 int ba_lm_phase_decide(ba_engine* e, void* stream);
 /* Copy the control block to the host (synchronises `stream`). */
 int ba_lm_state_get(ba_engine* e, ba_lm_state* out, void* stream);
+/* The same without stalling the stream: _post enqueues the copy into pinned slot `slot` (0 or 1)
+ * and an event behind it, _wait blocks the host on that event only.  A loop that posts after
+ * every decide and waits one solve later keeps the device one solve ahead of the host (every
+ * kernel of a solve is a no-op once the control block says done). */
+int ba_lm_state_post(ba_engine* e, int slot, void* stream);
+int ba_lm_state_wait(ba_engine* e, int slot, ba_lm_state* out);
 /* Run inner solves until one iteration is accepted or the loop terminates (single engine). */
 int ba_lm_iterate(ba_engine* e, ba_lm_state* out, void* stream);
 /* Whole optimize() loop (:102-195) for a single engine; records[0..*n_records) receive one

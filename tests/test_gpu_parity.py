@@ -128,6 +128,9 @@ def test_kernels_match_oracle_on_golden_cases(ba, name):
     (120, 900, 1.0, "x-right_z-forward"),   # dense, 128-wide SYRK tiles, multi-panel Cholesky
     (40, 2000, 0.3, "x-up_z-forward"),      # sparse path
     (17, 333, 1.0, "x-up_z-forward"),       # ragged sizes (nothing a multiple of anything)
+    (70, 3000, 0.9, "x-up_z-forward"),      # sparse path, nearly full bitmaps: multi-pass hit queue, 3 x 3 pair tiles
+    (33, 200, 0.5, "x-right_z-forward"),    # sparse path, one camera beyond a pair tile, single bitmap batch
+    (5, 9000, 0.7, "x-up_z-forward"),       # sparse path, few cameras, several bitmap batches per pair
 ])
 def test_kernels_match_oracle_on_random_scenes(ba, n_cams, n_points, visibility, axis):
     sc = ba.scenes.make_scene(n_cams, n_points, seed=n_cams, visibility=visibility, axis=axis)
@@ -170,6 +173,35 @@ def test_full_run_matches_reference_golden(ba, name, debug):
         np.testing.assert_allclose([d["reprojection_error"] for d in log], g["E"], rtol=1e-9)
     else:
         assert adj.get_log() == []
+
+
+@pytest.mark.parametrize("visibility", [1.0, 0.4])
+def test_graph_loop_equals_eager_loop(ba, visibility, monkeypatch):
+    """ba_lm_run replays one captured CUDA graph per inner solve, one solve ahead of the host;
+    BA_NO_GRAPH=1 keeps the launches eager.  Same kernels, same order: bit-identical records,
+    also when the engine (and its graphs) is reused for a second run."""
+    import os
+
+    sc = ba.scenes.make_scene(12, 400, seed=5, visibility=visibility)
+    runs = []
+    for no_graph in (False, True, False):
+        if no_graph:
+            monkeypatch.setenv("BA_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("BA_NO_GRAPH", raising=False)
+        assert (os.environ.get("BA_NO_GRAPH") == "1") == no_graph
+        adj = ba.BundleAdjuster.from_observations(sc.obs_ptr, sc.obs_cam, sc.obs_xy, sc.X0, sc.K0, sc.R0,
+                                                  sc.t0, f0=sc.f0, axis=sc.axis, dense=sc.dense)
+        eng = adj.engine
+        for rep in range(2):
+            eng.set_state(adj._X, adj._R, adj._t, adj._f, adj._u)
+            recs, st = eng.lm_run(2.0, 1e-8, 30)
+            runs.append(([(r.E_prev, r.E, r.c, r.solves) for r in recs], st.solves, eng.get_state(0)[0].copy()))
+        eng.close()
+    for other in runs[1:]:
+        assert other[0] == runs[0][0]
+        assert other[1] == runs[0][1]
+        assert np.array_equal(other[2], runs[0][2])
 
 
 def test_inputs_are_not_written(ba):
