@@ -14,6 +14,10 @@ def __getattr__(name):
         from . import bundle_adjuster
 
         return getattr(bundle_adjuster, name)
+    if name in ("calc_projected_points", "project_all"):
+        from . import projection
+
+        return getattr(projection, name)
     if name == "Engine":
         from . import engine
 

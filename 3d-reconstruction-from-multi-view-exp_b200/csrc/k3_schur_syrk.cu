@@ -240,6 +240,14 @@ int syrk_choose_splits(int n_pad, int tile, int64_t k_pad, int num_sms) {
   if (s_max < 1) s_max = 1;
   int64_t s_cap = (int64_t)24 * slots / n_tiles;
   if (s_cap < 1) s_cap = 1;
+  // All tiles of one split stream the same k-slab of Yt (k_pad / splits rows x n_pad columns).
+  // Tiles drift apart (diagonal and edge tiles do less work), so the slab is only served from L2
+  // if it fits there as a whole: ncu showed 18.6 GB of DRAM reads for the 4.3 GB operand of C3
+  // with 271 MB slabs.  Ask for slabs of at most 48 MB (of the 126 MB L2) when K allows it.
+  const int64_t slab_cap = (int64_t)48 << 20;
+  int64_t s_l2 = ((int64_t)k_pad * n_pad * 8 + slab_cap - 1) / slab_cap;
+  if (s_l2 > s_max) s_l2 = s_max;
+  if (s_cap < s_l2) s_cap = s_l2;
   const int s_hi = (int)(s_max < s_cap ? s_max : s_cap);
   int best = s_hi;
   double best_eff = 0.0;

@@ -195,6 +195,15 @@ int ba_profile_reset(ba_engine* e);
 /* FP64 peak micro-benchmarks (register-resident DMMA.8x8x4 / DFMA loops): TFLOP/s. */
 int ba_fp64_peak(int device, int use_dmma, double* tflops);
 
+/* ---- next to the path: batched re-projection ------------------------------------------- */
+/* calc_projected_points (reference lib/camera.py:74-81, Camera.project_points :18-32): project
+ * X[n_points][3] into every camera (K[n_cams][3][3] general, R camera-to-world, t centres);
+ * out[n_cams][n_points][2] = (p/r, q/r).  No engine needed.  With BA_MEM_HOST the call copies
+ * in, computes, copies out and synchronises `stream`; with BA_MEM_DEVICE all five pointers are
+ * device pointers (out 16-byte aligned) and the call is asynchronous. */
+int ba_project_points(int device, int64_t n_points, int32_t n_cams, const double* X, const double* K,
+                      const double* R, const double* t, double* out, int mem, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -376,3 +376,21 @@ class OracleBundleAdjuster:
 
     def get_log(self):
         return self._log
+
+
+# ---- batched re-projection (reference lib/camera.py:13, :28-32, :74-81) -----------------------
+def project_all(X, K, R, t):
+    """``calc_projected_points`` for all cameras at once: ``(M, N, 2)``.
+
+    Per camera P = K [R^T | -R^T t] (``get_camera_matrix``, :13), X_ext @ P^T, then the
+    perspective division by the third component (``_perspective_projection``, :28-32)."""
+    X = np.asarray(X, dtype=np.float64)
+    K = np.asarray(K, dtype=np.float64)
+    R = np.asarray(R, dtype=np.float64)
+    t = np.asarray(t, dtype=np.float64)
+    Rt = np.transpose(R, (0, 2, 1))
+    E = np.concatenate([Rt, -(Rt @ t[:, :, None])], axis=2)  # (M, 3, 4)
+    P = K @ E
+    X_ext = np.hstack([X, np.ones((X.shape[0], 1))])
+    proj = np.einsum("nc,mrc->mnr", X_ext, P)
+    return proj[:, :, :2] / proj[:, :, 2:3]
