@@ -15,7 +15,9 @@ import numpy as np
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libba_b200.so")
 
-BA_OK, BA_ERR_INVALID, BA_ERR_CUDA, BA_ERR_SINGULAR, BA_ERR_STATE, BA_ERR_NO_DEVICE, BA_ERR_STALL = range(7)
+(BA_OK, BA_ERR_INVALID, BA_ERR_CUDA, BA_ERR_SINGULAR, BA_ERR_STATE, BA_ERR_NO_DEVICE, BA_ERR_STALL,
+ BA_ERR_COMM) = range(8)
+BA_COMM_HANDLE_BYTES = 64
 BA_MEM_HOST, BA_MEM_DEVICE = 0, 1
 BA_AXIS_X_RIGHT, BA_AXIS_X_UP = 0, 1
 AXIS_CODES = {"x-right_z-forward": BA_AXIS_X_RIGHT, "x-up_z-forward": BA_AXIS_X_UP}
@@ -74,6 +76,10 @@ SIGNATURES = {
     "ba_buffer_size": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64)]),
     "ba_buffer_read": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P]),
     "ba_reduced_layout": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ba_comm_create": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "ba_comm_connect": (C.c_int, [_P, _P]),
+    "ba_comm_disconnect": (C.c_int, [_P]),
+    "ba_comm_world": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ba_launch_count": (C.c_int64, []),
     "ba_profile_enable": (C.c_int, [_P, C.c_int]),
     "ba_profile_get": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

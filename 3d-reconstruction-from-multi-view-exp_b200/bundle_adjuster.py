@@ -5,8 +5,11 @@ and exception types; the Levenberg-Marquardt loop itself runs on the GPU behind 
 Additions that the reference does not have (all keyword-only / separate constructors):
   * ``BundleAdjuster.from_observations`` -- observation-list (CSR by point) ingestion, so the
     1000 x 1M sparse configurations never build the dense ``(N, M, 2)`` array;
-  * ``process_group`` -- points sharded over ranks (one engine per GPU); two NCCL all-reduces
-    per inner solve (partial reduced system, trial cost);
+  * ``process_group`` -- points sharded over ranks (one engine per GPU); per inner solve the
+    partial reduced system and the trial cost are summed over the ranks, by default
+    (``exchange="peer"`` whenever the group runs on NCCL, i.e. one GPU per rank) by the
+    library's own kernels over NVLink peer memory, otherwise (``exchange="collective"``) by
+    two ``torch.distributed`` all-reduces;
   * ``max_retries`` -- a cap on inner solves per iteration (the reference loops forever, :118).
 """
 from __future__ import annotations
@@ -55,7 +58,8 @@ class ObservationList:
 class BundleAdjuster:
     def __init__(self, x, init_X, init_K, init_R, init_t, f0=1.0, visibility_index=None,
                  axis="x-right_z-forward", *, observations: ObservationList | None = None,
-                 device: int | None = None, process_group=None, max_retries: int = 200):
+                 device: int | None = None, process_group=None, max_retries: int = 200,
+                 exchange: str = "auto"):
         gauge.axis_component(axis)  # ValueError() for an unknown axis (:28)
         init_X = np.asarray(init_X, dtype=np.float64)
         init_R = np.asarray(init_R, dtype=np.float64)
@@ -92,6 +96,19 @@ class BundleAdjuster:
         self._engine = Engine(self._n_points, self._n_images, obs.n_obs, self._f0, axis, obs.dense, device)
         self._engine.set_observations(obs.obs_ptr, obs.obs_cam, obs.obs_xy)
         self._engine.set_state(self._X, self._R, self._t, self._f, self._u)
+        self._peer_exchange = False
+        self._quiet = False  # sharded runs: only rank 0 prints the iteration lines (:188)
+        if exchange not in ("auto", "peer", "collective"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'collective'")
+        if process_group is not None and exchange != "collective":
+            import torch.distributed as dist
+
+            world = dist.get_world_size(process_group)
+            if exchange == "peer" or (str(dist.get_backend(process_group)) == "nccl" and 2 <= world <= 8):
+                if world >= 2:
+                    self._engine.comm_attach(dist, process_group)
+                    self._peer_exchange = True
+                    self._quiet = dist.get_rank(process_group) != 0
 
     @classmethod
     def from_observations(cls, obs_ptr, obs_cam, obs_xy, init_X, init_K, init_R, init_t, f0=1.0,
@@ -111,7 +128,7 @@ class BundleAdjuster:
         """Minimise the reprojection error over X, K, R, t (reference :77-202)."""
         eng = self._engine
         self.records = []
-        if self._group is not None:
+        if self._group is not None and not self._peer_exchange:
             from .sharded import run_sharded
 
             run_sharded(self, scale_factor, delta_tol, max_iter, is_debug)
@@ -143,7 +160,8 @@ class BundleAdjuster:
     def _record(self, E_prev, E, delta, c, solves, count):
         self.records.append({"E_prev": E_prev, "E": E, "delta": delta, "c": c, "solves": solves,
                              "count": count})
-        print(f"Iteration {count}: reprojection_error_delta = {np.float64(delta)}")  # :188
+        if not self._quiet:
+            print(f"Iteration {count}: reprojection_error_delta = {np.float64(delta)}")  # :188
 
     def _log_state(self, E):
         X, R, t, _, _ = self._engine.get_state(0)

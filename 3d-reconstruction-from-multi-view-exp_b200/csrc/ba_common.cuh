@@ -44,6 +44,7 @@ constexpr int kPT = 12;       // doubles per point in the pair kernel's point ta
                               // X (3), damped V^-1 (00 01 02 11 12 22), 3 pad = 96 B = 3 sectors
 constexpr int kCholNB = 64;   // panel width of the blocked Cholesky
 constexpr int kMaxRecords = 4096;
+constexpr int kMaxRanks = 8;    // ranks of one peer-memory exchange (one NVSwitch domain)
 
 // Pinned camera parameters (gauge): camera 0 keeps f,u0,v0 only; camera 1 loses one
 // translation component (reference lib/bundle_adjustment.py:62-72).  Bit a set = parameter a
@@ -61,7 +62,9 @@ struct CamState {
 
 // "k3" brackets the whole Schur phase; "syrk" only the DMMA kernel inside it (nested scopes
 // use their own event pair).
-enum ProfGroup { PG_K1 = 0, PG_K2, PG_K3, PG_K4, PG_COST, PG_OTHER, PG_SYRK, PG_CHOL, PG_COUNT };
+enum ProfGroup { PG_K1 = 0, PG_K2, PG_K3, PG_K4, PG_COST, PG_OTHER, PG_SYRK, PG_CHOL, PG_COMM, PG_COUNT };
+
+struct Comm;  // peer-memory exchange of a sharded run (comm_peer.cu)
 
 struct ProfSlot {
   double ms = 0.0;
@@ -113,6 +116,8 @@ struct ba_engine {
   double* PT = nullptr;   // sparse: [N][kPT] point table of the pair kernel (X, damped V^-1)
   double* red = nullptr;  // [n_pad*n_pad | M*81 | M*9]
   int64_t red_len = 0;
+  bool red_in_window = false;  // red lives in the exchange window (freed with it)
+  ba::Comm* comm = nullptr;    // non-null: sharded run, sums go through peer memory
   double* Spart = nullptr;  // split-K partial tiles
   double* Lt = nullptr;     // Cholesky panel, k-major copy [kCholNB][n_pad]
   double* Winv = nullptr;   // [panels][64][64] L_D^-T of every diagonal block (back substitution)
@@ -229,5 +234,8 @@ int build_camera_major_index(ba_engine* e, cudaStream_t s);
 int build_pair_index(ba_engine* e, cudaStream_t s);
 int launch_schur_sparse(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s);
 int fp64_peak(int device, int use_dmma, double* tflops);
+int launch_comm_allreduce_red(ba_engine* e, bool conditional, cudaStream_t s);
+int launch_comm_allreduce_cost(ba_engine* e, int slot, bool conditional, cudaStream_t s);
+void comm_free(ba_engine* e);
 
 }  // namespace ba

@@ -151,9 +151,11 @@ int build_camera_major_index(ba_engine* e, cudaStream_t s) {
 static void free_engine(ba_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
+  if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+  comm_free(e);  // closes the peers' windows and frees this rank's (which holds red)
   void* ptrs[] = {e->obs_ptr, e->obs_cam, e->obs_pt, e->obs_xy, e->cam_ptr, e->cm_perm, e->bits, e->PT, e->X[0],
                   e->X[1], e->cam[0].f, e->cam[1].f, e->camtab[0], e->camtab[1], e->JP, e->JC, e->V,
-                  e->GPT, e->Upart, e->Uloc, e->LINV, e->Z, e->Yt, e->Ysp, e->red, e->Spart, e->Lt, e->Winv,
+                  e->GPT, e->Upart, e->Uloc, e->LINV, e->Z, e->Yt, e->Ysp, e->red_in_window ? nullptr : e->red, e->Spart, e->Lt, e->Winv,
                   e->dxi, e->cost_part, e->cost_buf, e->ctl, e->rec};
   for (void* p : ptrs)
     dev_free(p);
@@ -341,6 +343,7 @@ static int phase_reduce(ba_engine* e, bool conditional, double c_host, cudaStrea
   }
   { ProfScope ps(e, PG_K2, s); BA_TRY(launch_k2b(e, conditional, c_host, s)); }
   { ProfScope ps(e, PG_K3, s); BA_TRY(launch_k3(e, conditional, s)); }
+  if (e->comm) BA_TRY(launch_comm_allreduce_red(e, conditional, s));
   return BA_OK;
 }
 
@@ -349,6 +352,7 @@ static int phase_solve(ba_engine* e, bool conditional, double c_host, cudaStream
   BA_TRY(launch_assemble(e, conditional, c_host, s));
   { ProfScope pc(e, PG_CHOL, s); BA_TRY(launch_cholesky_solve(e, conditional, s)); }
   BA_TRY(launch_update_trial(e, conditional, s));
+  if (e->comm) BA_TRY(launch_comm_allreduce_cost(e, 1, conditional, s));
   return BA_OK;
 }
 
@@ -363,6 +367,10 @@ static int status_from_ctl(const ba_lm_state& st) {
   if (st.status == BA_ERR_SINGULAR) {
     set_error("Singular matrix");  // numpy.linalg.LinAlgError text of the reference (:128)
     return BA_ERR_SINGULAR;
+  }
+  if (st.status == BA_ERR_COMM) {
+    set_error("a peer rank did not answer within the spin limit of the NVLink exchange");
+    return BA_ERR_COMM;
   }
   if (st.status == BA_ERR_STALL) {
     set_error("inner LM loop exceeded %d retries without decreasing the cost", st.max_retries);
@@ -497,9 +505,13 @@ int ba_lm_begin(ba_engine* e, double scale_factor, double delta_tol, int max_ite
   cudaStream_t s = (cudaStream_t)stream;
   if (max_retries <= 0) max_retries = 200;
   BA_TRY(launch_lm_begin(e, scale_factor, delta_tol, max_iter, max_retries, s));
-  ProfScope ps(e, PG_COST, s);
-  BA_TRY(launch_cam_prep(e, 0, s));
-  return launch_cost(e, 0, 0, s);
+  {
+    ProfScope ps(e, PG_COST, s);
+    BA_TRY(launch_cam_prep(e, 0, s));
+    BA_TRY(launch_cost(e, 0, 0, s));
+  }
+  if (e->comm) BA_TRY(launch_comm_allreduce_cost(e, 0, true, s));
+  return BA_OK;
 }
 
 int ba_lm_phase_reduce(ba_engine* e, void* stream) {
@@ -728,7 +740,7 @@ int ba_profile_enable(ba_engine* e, int on) {
 }
 
 static int group_id(const char* g) {
-  static const char* names[PG_COUNT] = {"k1", "k2", "k3", "k4", "cost", "other", "syrk", "chol"};
+  static const char* names[PG_COUNT] = {"k1", "k2", "k3", "k4", "cost", "other", "syrk", "chol", "comm"};
   for (int i = 0; i < PG_COUNT; ++i)
     if (g && std::strcmp(g, names[i]) == 0) return i;
   return -1;

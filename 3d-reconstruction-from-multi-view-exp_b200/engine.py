@@ -68,6 +68,16 @@ class Engine:
     # -- life cycle ---------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
+            comm = getattr(self, "_comm", None)
+            if comm is not None:
+                # unmap the peers' windows, then wait until every rank has done so before this
+                # rank's window is freed (collective: all ranks close their engines together)
+                self._comm = None
+                self._lib.ba_comm_disconnect(self._h)
+                try:
+                    comm[0].barrier(comm[1])
+                except Exception:  # process group already gone (interpreter shutdown)
+                    pass
             self._lib.ba_destroy(self._h)
             self._h = None
 
@@ -179,6 +189,33 @@ class Engine:
         _cabi.check(status)
         return [recs[i] for i in range(n.value)], st
 
+    # -- sharded runs: sums over NVLink peer memory ---------------------------------------------
+    def comm_attach(self, dist, group=None) -> None:
+        """Connect this engine with the engines of the other ranks of `group` (one process per
+        GPU, all on one box): every rank exports its exchange window as a CUDA IPC handle, the
+        handles are gathered over ``torch.distributed`` (plumbing only) and mapped.  Afterwards
+        ``lm_begin`` / ``lm_phase_*`` / ``lm_iterate`` / ``lm_run`` sum the partial reduced
+        system and the costs over the ranks inside the library (``csrc/comm_peer.cu``)."""
+        import torch
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        handle = (C.c_ubyte * _cabi.BA_COMM_HANDLE_BYTES)()
+        _cabi.check(self._lib.ba_comm_create(self._h, rank, world, handle))
+        on_gpu = str(dist.get_backend(group)) == "nccl"
+        dev = f"cuda:{self.device}" if on_gpu else "cpu"
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=dev)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=group)
+        blob = b"".join(t.cpu().numpy().tobytes() for t in gathered)
+        _cabi.check(self._lib.ba_comm_connect(self._h, blob))
+        dist.barrier(group)  # nobody stores into a window before every rank has mapped them all
+        self._comm = (dist, group)
+
+    def comm_size(self) -> int:
+        r, w = C.c_int(), C.c_int()
+        _cabi.check(self._lib.ba_comm_world(self._h, C.byref(r), C.byref(w)))
+        return w.value
+
     # -- buffers ------------------------------------------------------------------------------
     def _device_tensor(self, getter):
         import torch
@@ -212,7 +249,7 @@ class Engine:
 
     def profile(self) -> dict:
         out = {}
-        for g in ("k1", "k2", "k3", "k4", "cost", "other", "syrk", "chol"):
+        for g in ("k1", "k2", "k3", "k4", "cost", "other", "syrk", "chol", "comm"):
             ms, n = C.c_double(), C.c_int64()
             _cabi.check(self._lib.ba_profile_get(self._h, g.encode(), C.byref(ms), C.byref(n)))
             out[g] = {"ms": ms.value, "launches": n.value}

@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "collective"],
+                    help="N > 1: how the ranks sum the partial reduced system and the cost: the library's "
+                         "own kernels over NVLink peer memory (auto/peer) or torch.distributed all-reduces")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: the named scene's points are split over the ranks "
                          "(default: weak, every rank owns a full named scene)")
@@ -67,7 +70,7 @@ def workload_config(name: str) -> dict:
     return cfg
 
 
-def describe(name: str, cfg: dict, world: int, nobs_total: int) -> dict:
+def describe(name: str, cfg: dict, world: int, nobs_total: int, exchange: str = "") -> dict:
     vis = cfg.get("visibility", 1.0)
     return {
         "workload": f"{name}: synthetic {cfg['n_cams']} cameras x {cfg['n_points']} points per GPU, "
@@ -76,7 +79,7 @@ def describe(name: str, cfg: dict, world: int, nobs_total: int) -> dict:
         "n_cams": cfg["n_cams"], "n_points_per_gpu": cfg["n_points"], "observations_total": nobs_total,
         "unknowns_reduced": 9 * cfg["n_cams"] - 7,
         "lm": "optimize(scale_factor=2.0), one step = one accepted LM iteration from the perturbed start",
-        "parallelism": f"points sharded over {world} GPU(s), cameras replicated" if world > 1 else "single GPU",
+        "parallelism": f"points sharded over {world} GPU(s), cameras replicated; {exchange}" if world > 1 else "single GPU",
         "l2": "no flush: iterations are data-dependent; per-iteration working set "
               "(Jacobian rows + Y) exceeds the 126 MB L2 for c2 and larger",
     }
@@ -218,7 +221,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     def make_adjuster():
         return ba_b200.BundleAdjuster.from_observations(
             h_ptr, h_cam, h_xy, h_X0, h_K0, h_R0, h_t0, f0=sc.f0, axis=sc.axis, dense=sc.dense,
-            device=local_rank, process_group=group)
+            device=local_rank, process_group=group, exchange=args.exchange)
 
     def barrier():
         if dist is not None:
@@ -229,7 +232,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
         """Exactly n accepted LM iterations from the adjuster's stored initial state."""
         eng = adj.engine
         eng.set_state(adj._X, adj._R, adj._t, adj._f, adj._u)
-        if world > 1:
+        if world > 1 and not adj._peer_exchange:
             return sharded.lm_loop(eng, dist, group, SCALE, TOL_NEVER, n)
         _, st = eng.lm_run(SCALE, TOL_NEVER, n)
         return st
@@ -271,7 +274,10 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": describe(args.workload, cfg, world, nobs_total),
+            "dtype": "f64", "data": "synthetic",
+            "config": describe(args.workload, cfg, world, nobs_total,
+                               "sums over NVLink peer memory by the library's kernels (CUDA-graph loop)"
+                               if adj._peer_exchange else "two NCCL all-reduces per solve"),
             "lm_iterations_per_s": K / (ms * 1e-3), "inner_solves": int(st.solves), "final_rms": final_rms,
             "gpu_launches": int(launches),
         }

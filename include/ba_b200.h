@@ -43,8 +43,9 @@ typedef enum ba_status {
   BA_ERR_SINGULAR = 3,  /* singular point block     -> LinAlgError  (reference :128, :146)  */
   BA_ERR_STATE = 4,     /* call out of order        -> RuntimeError                         */
   BA_ERR_NO_DEVICE = 5, /* no CUDA device           -> RuntimeError (there is no CPU path)  */
-  BA_ERR_STALL = 6      /* inner LM loop exceeded max_retries -> RuntimeError (the reference
+  BA_ERR_STALL = 6,     /* inner LM loop exceeded max_retries -> RuntimeError (the reference
                            loops forever, :118; documented deviation)                       */
+  BA_ERR_COMM = 7       /* a peer rank did not answer within the spin limit -> RuntimeError  */
 } ba_status;
 
 enum { BA_MEM_HOST = 0, BA_MEM_DEVICE = 1 };
@@ -163,6 +164,24 @@ int ba_cost_buffer(ba_engine* e, void** device_ptr, int64_t* n_doubles);
 /* Only one rank prints/logs; every rank must still hold the same U/dF: this marks whether
  * this engine's U/dF partials are to be counted (all ranks: 1). */
 
+/* ---- sharded runs over NVLink peer memory (one process per GPU, <= 8 ranks of one box) --- */
+/* The reference is a single process (no parallelism of any kind); these
+ * calls are the multi-GPU form of the sums at :135-143 and :674-676.  ba_comm_create allocates
+ * this rank's exchange window (header + reduce buffer + one staging slot per rank), moves the
+ * reduce buffer into it and returns the window's CUDA IPC handle (BA_COMM_HANDLE_BYTES bytes).
+ * The host gathers the handles of all ranks in rank order (any transport; e.g.
+ * torch.distributed.all_gather) and passes them to ba_comm_connect, then synchronises the ranks
+ * once.  From then on ba_lm_begin / ba_lm_phase_* / ba_lm_iterate / ba_lm_run sum the partial
+ * reduced system and the costs over all ranks with the library's own kernels (peer stores,
+ * deterministic rank-order addition); the host must NOT all-reduce the buffers as well. */
+#define BA_COMM_HANDLE_BYTES 64
+int ba_comm_create(ba_engine* e, int rank, int world, void* handle_out);
+int ba_comm_connect(ba_engine* e, const void* handles /* world x BA_COMM_HANDLE_BYTES */);
+/* Unmap the other ranks' windows.  Every rank calls this, the host synchronises the ranks, and
+ * only then are the engines destroyed (a window must not be freed while a peer still maps it). */
+int ba_comm_disconnect(ba_engine* e);
+int ba_comm_world(ba_engine* e, int* rank, int* world);
+
 /* ---- inspection (tests, ncu-free evidence); copies to host memory ------------------- */
 typedef enum ba_buffer_id {
   BA_BUF_JP = 0,     /* [n_obs][8]  e0,e1, d e/dX (2x3)                    K1   */
@@ -188,7 +207,8 @@ int ba_reduced_layout(ba_engine* e, int32_t* n_pad, int32_t* n_full, int32_t* rh
 int64_t ba_launch_count(void);
 /* Device time (ms, CUDA events on `stream`) and launches of the named kernel group
  * accumulated while profiling is enabled; groups: "k1","k2","k3","k4","cost","other", and
- * nested inside k3 / k4: "syrk" (the DMMA kernel alone), "chol" (factor + solve). */
+ * nested inside k3 / k4: "syrk" (the DMMA kernel alone), "chol" (factor + solve), "comm" (the
+ * peer-memory sums of a sharded run). */
 int ba_profile_enable(ba_engine* e, int on);
 int ba_profile_get(ba_engine* e, const char* group, double* total_ms, int64_t* launches);
 int ba_profile_reset(ba_engine* e);

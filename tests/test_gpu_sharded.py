@@ -1,7 +1,15 @@
-"""Sharded CUDA path on ONE GPU: two ranks (processes) share cuda:0, each owns half of the
-points, and the two all-reduces per inner solve go through gloo (NCCL needs one GPU per rank;
-the multi-GPU NCCL run is exercised by `bench.py --gpus N`).  Checks the engine's phase API
-(`ba_lm_phase_*`, reduce / cost buffers) against the reference's golden trajectory."""
+"""Sharded CUDA path: two ranks (processes), each owns half of the points.
+
+* exchange="collective": the two sums per inner solve are `torch.distributed` all-reduces (gloo
+  here, both ranks share cuda:0; NCCL needs one GPU per rank and is exercised by
+  `bench.py --gpus N --exchange collective`).  Checks the phase API (`ba_lm_phase_*`, reduce /
+  cost buffers).
+* exchange="peer": the sums are formed by the library's own kernels over peer memory (CUDA IPC
+  windows, `csrc/comm_peer.cu`) and the loop is the same CUDA-graph loop as on one GPU.  Runs with
+  one GPU per rank when the box has two (NVLink), and with both ranks time-sliced on cuda:0
+  otherwise (the protocol is the same; only the transport differs).
+
+Both are checked against the reference's golden trajectory."""
 import os
 import socket
 import sys
@@ -13,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, case, out_dir):
+def _worker(rank, world, port, case, out_dir, exchange="collective", per_rank_gpu=False):
     import contextlib
     import io
 
@@ -22,7 +30,8 @@ def _worker(rank, world, port, case, out_dir):
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(0)
+    dev = rank if per_rank_gpu else 0
+    torch.cuda.set_device(dev)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         sys.path.insert(0, ROOT)
@@ -40,8 +49,10 @@ def _worker(rank, world, port, case, out_dir):
         adj = ba_b200.BundleAdjuster.from_observations(
             full.obs_ptr[lo:hi + 1] - full.obs_ptr[lo],
             None if full.dense else full.obs_cam[a:b], full.obs_xy[a:b],
-            X0[lo:hi], K0, R0, t0, f0=f0, axis=axis, dense=full.dense, device=0,
-            process_group=dist.group.WORLD)
+            X0[lo:hi], K0, R0, t0, f0=f0, axis=axis, dense=full.dense, device=dev,
+            process_group=dist.group.WORLD, exchange=exchange)
+        assert adj._peer_exchange == (exchange == "peer")
+        assert adj.engine.comm_size() == (world if exchange == "peer" else 1)
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):
             X, K, R, t = adj.optimize(2.0, 1e-8, max_iter=100, is_debug=(rank == 0))
@@ -49,6 +60,7 @@ def _worker(rank, world, port, case, out_dir):
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), E=E, X=X, K=K, R=R, t=t, lo=lo, hi=hi,
                  lines=len(buf.getvalue().strip().splitlines()),
                  nlog=len(adj.get_log()))
+        adj.engine.close()
     finally:
         dist.destroy_process_group()
 
@@ -59,15 +71,19 @@ def _free_port():
         return s.getsockname()[1]
 
 
+@pytest.mark.parametrize("exchange", ["collective", "peer"])
 @pytest.mark.parametrize("case", ["small_sparse_xup", "mid_dense_xup"])
-def test_two_ranks_on_one_gpu_match_reference(tmp_path, case):
+def test_two_ranks_match_reference(tmp_path, case, exchange):
+    import torch
     import torch.multiprocessing as mp
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from conftest import load_golden
 
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), case, str(tmp_path)), nprocs=world, join=True)
+    per_rank_gpu = exchange == "peer" and torch.cuda.device_count() >= world
+    mp.spawn(_worker, args=(world, _free_port(), case, str(tmp_path), exchange, per_rank_gpu),
+             nprocs=world, join=True)
     g = load_golden(case)
     out = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
     X = np.zeros_like(g["X"])
