@@ -31,6 +31,9 @@
 // polled with ld.acquire.sys; staged data is read with ld.global.cg (L2 only).  Every spin has a
 // wall-clock limit: a missing peer turns into BA_ERR_COMM instead of a hung GPU.
 #include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
 
 #include "ba_common.cuh"
 
@@ -58,14 +61,6 @@ struct CommDev {
   CommHeader* hdr[kMaxRanks];
   double* red[kMaxRanks];
   double* stage[kMaxRanks];  // stage[o] + src * red_len
-};
-
-struct Comm {
-  CommDev dev{};
-  void* window = nullptr;            // own window
-  void* peer_base[kMaxRanks] = {};   // opened IPC mappings (null for self)
-  size_t window_bytes = 0;
-  bool connected = false;
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
@@ -249,6 +244,38 @@ __global__ void comm_small_kernel(CommDev cd, double* cost_buf, int slot, ba_lm_
 // ---- host side --------------------------------------------------------------------------------
 static inline int64_t round_up_i64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
+// Windows outlive engines: allocating, exporting and mapping a window costs milliseconds (and a
+// multi-gigabyte cudaFree synchronises the device), more than a whole small adjustment.  A rank
+// that creates engine after engine of the same shape -- the usual way the reference's class is
+// used -- therefore gets its previous window back, with the peers' mappings still open and the
+// epochs simply continuing.  Every rank runs the same sequence of creations, so all ranks hit or
+// miss together; the handshake blob carries the epochs and ba_comm_connect refuses windows that
+// are out of step.
+struct Window {
+  int device = 0, rank = 0, world = 0, n_pad = 0;
+  int64_t red_len = 0;
+  void* base = nullptr;
+  size_t bytes = 0;
+  cudaIpcMemHandle_t handle{};
+  cudaIpcMemHandle_t peer_handle[kMaxRanks]{};
+  void* peer_base[kMaxRanks] = {};
+  bool mapped = false, in_use = false;
+};
+static std::mutex g_win_mutex;
+static std::vector<Window*> g_windows;
+
+struct Comm {
+  CommDev dev{};
+  Window* win = nullptr;
+  bool connected = false;
+};
+
+struct HandshakeBlob {
+  cudaIpcMemHandle_t handle;
+  unsigned long long epoch, epoch_small;
+};
+static_assert(sizeof(HandshakeBlob) == BA_COMM_HANDLE_BYTES, "handshake blob size");
+
 int launch_comm_allreduce_red(ba_engine* e, bool conditional, cudaStream_t s) {
   Comm* c = e->comm;
   if (!c || !c->connected) { set_error("exchange window not connected"); return BA_ERR_STATE; }
@@ -275,13 +302,15 @@ int launch_comm_allreduce_cost(ba_engine* e, int slot, bool conditional, cudaStr
   return BA_OK;
 }
 
+// The engine lets go of its window; the window (and the peers' mappings) stay for the next engine.
 void comm_free(ba_engine* e) {
   Comm* c = e->comm;
   if (!c) return;
   cudaDeviceSynchronize();
-  for (int p = 0; p < kMaxRanks; ++p)
-    if (c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
-  if (c->window) cudaFree(c->window);
+  {
+    std::lock_guard<std::mutex> lock(g_win_mutex);
+    if (c->win) c->win->in_use = false;
+  }
   delete c;
   e->comm = nullptr;
 }
@@ -310,17 +339,40 @@ static int comm_create(ba_engine* e, int rank, int world) {
   const int64_t tail = e->red_len - (int64_t)e->n_pad * e->n_pad;
   c->dev.n_seg = e->n_pad + (int)((tail + e->n_pad - 1) / e->n_pad);
   const int64_t red_bytes = round_up_i64(e->red_len * (int64_t)sizeof(double), 256);
-  // stage slots keep the red layout (stage[src][idx]); only the owned lower-triangle segments of
-  // each slot are ever touched
-  c->window_bytes = kHeaderBytes + (size_t)red_bytes + (size_t)world * (size_t)e->red_len * sizeof(double);
-  cudaError_t err = cudaMalloc(&c->window, c->window_bytes);
-  if (err != cudaSuccess) {
-    set_error("cudaMalloc of the %zu-byte exchange window failed: %s", c->window_bytes, cudaGetErrorString(err));
-    delete c;
-    return BA_ERR_CUDA;
+  Window* w = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_win_mutex);
+    for (Window* cand : g_windows)
+      if (!cand->in_use && cand->device == e->device && cand->rank == rank && cand->world == world &&
+          cand->red_len == e->red_len && cand->n_pad == e->n_pad) {
+        w = cand;
+        w->in_use = true;
+        break;
+      }
   }
-  cudaMemset(c->window, 0, kHeaderBytes + (size_t)red_bytes);
-  fill_rank(c, rank, c->window);
+  if (!w) {
+    w = new (std::nothrow) Window();
+    if (!w) { delete c; set_error("out of host memory"); return BA_ERR_CUDA; }
+    w->device = e->device; w->rank = rank; w->world = world; w->n_pad = e->n_pad; w->red_len = e->red_len;
+    // stage slots keep the red layout (stage[src][idx]); only the owned lower-triangle segments
+    // of each slot are ever touched
+    w->bytes = kHeaderBytes + (size_t)red_bytes + (size_t)world * (size_t)e->red_len * sizeof(double);
+    cudaError_t err = cudaMalloc(&w->base, w->bytes);
+    if (err == cudaSuccess) err = cudaMemset(w->base, 0, kHeaderBytes);
+    if (err == cudaSuccess) err = cudaIpcGetMemHandle(&w->handle, w->base);
+    if (err != cudaSuccess) {
+      set_error("exchange window of %zu bytes: %s", w->bytes, cudaGetErrorString(err));
+      if (w->base) cudaFree(w->base);
+      delete w;
+      delete c;
+      return BA_ERR_CUDA;
+    }
+    w->in_use = true;
+    std::lock_guard<std::mutex> lock(g_win_mutex);
+    g_windows.push_back(w);
+  }
+  c->win = w;
+  fill_rank(c, rank, w->base);
   e->comm = c;
   return BA_OK;
 }
@@ -342,45 +394,55 @@ int ba_comm_create(ba_engine* e, int rank, int world, void* handle_out) {
   e->red_in_window = true;
   for (int k = 0; k < 2; ++k)  // graphs captured before hold the old pointer
     if (e->solve_graph[k]) { cudaGraphExecDestroy(e->solve_graph[k]); e->solve_graph[k] = nullptr; }
-  BA_CUDA(cudaDeviceSynchronize());
-  cudaIpcMemHandle_t h;
-  BA_CUDA(cudaIpcGetMemHandle(&h, c->window));
-  static_assert(sizeof(h) == BA_COMM_HANDLE_BYTES, "IPC handle size");
-  std::memcpy(handle_out, &h, sizeof(h));
+  HandshakeBlob blob;
+  blob.handle = c->win->handle;
+  unsigned long long ep[2];
+  BA_CUDA(cudaMemcpy(ep, &c->dev.hdr[rank]->epoch, sizeof(ep), cudaMemcpyDeviceToHost));  // synchronises
+  blob.epoch = ep[0];
+  blob.epoch_small = ep[1];
+  std::memcpy(handle_out, &blob, sizeof(blob));
   return BA_OK;
 }
 
 int ba_comm_connect(ba_engine* e, const void* handles) {
   if (!e || !handles || !e->comm) { set_error("ba_comm_create must come first"); return BA_ERR_STATE; }
   Comm* c = e->comm;
+  Window* w = c->win;
   BA_CUDA(cudaSetDevice(e->device));
-  const char* hb = static_cast<const char*>(handles);
+  const HandshakeBlob* hb = static_cast<const HandshakeBlob*>(handles);
+  const HandshakeBlob& mine = hb[c->dev.rank];
+  for (int p = 0; p < c->dev.world; ++p)
+    if (hb[p].epoch != mine.epoch || hb[p].epoch_small != mine.epoch_small) {
+      set_error("exchange windows out of step: rank %d is at epoch %llu/%llu, rank %d at %llu/%llu "
+                "(all ranks must create and run their engines in the same order)",
+                p, hb[p].epoch, hb[p].epoch_small, c->dev.rank, mine.epoch, mine.epoch_small);
+      return BA_ERR_STATE;
+    }
   for (int p = 0; p < c->dev.world; ++p) {
     if (p == c->dev.rank) continue;
-    cudaIpcMemHandle_t h;
-    std::memcpy(&h, hb + (size_t)p * BA_COMM_HANDLE_BYTES, sizeof(h));
-    void* base = nullptr;
-    BA_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
-    c->peer_base[p] = base;
-    fill_rank(c, p, base);
+    const bool same = w->mapped && w->peer_base[p] &&
+                      std::memcmp(&w->peer_handle[p], &hb[p].handle, sizeof(cudaIpcMemHandle_t)) == 0;
+    if (!same) {
+      if (w->peer_base[p]) { cudaIpcCloseMemHandle(w->peer_base[p]); w->peer_base[p] = nullptr; }
+      void* base = nullptr;
+      BA_CUDA(cudaIpcOpenMemHandle(&base, hb[p].handle, cudaIpcMemLazyEnablePeerAccess));
+      w->peer_base[p] = base;
+      w->peer_handle[p] = hb[p].handle;
+    }
+    fill_rank(c, p, w->peer_base[p]);
   }
+  w->mapped = true;
   c->connected = true;
   return BA_OK;
 }
 
 int ba_comm_disconnect(ba_engine* e) {
   if (!e) { set_error("null engine"); return BA_ERR_INVALID; }
-  Comm* c = e->comm;
-  if (!c) return BA_OK;
+  if (!e->comm) return BA_OK;
   BA_CUDA(cudaSetDevice(e->device));
   if (e->own_stream) BA_CUDA(cudaStreamSynchronize(e->own_stream));
   BA_CUDA(cudaDeviceSynchronize());
-  for (int p = 0; p < kMaxRanks; ++p)
-    if (c->peer_base[p]) {
-      cudaIpcCloseMemHandle(c->peer_base[p]);
-      c->peer_base[p] = nullptr;
-    }
-  c->connected = false;
+  e->comm->connected = false;
   return BA_OK;
 }
 

@@ -15,6 +15,8 @@
 //                       W = L_D^-T for the back substitution (no serial solve there either).
 //                       Writes L rows in place and a k-major copy Lt for the update.
 //   chol_update_kernel  trailing update S -= L_panel L_panel^T on 64x64 tiles.
+#include <cstdlib>
+
 #include "ba_common.cuh"
 
 namespace ba {
@@ -212,6 +214,121 @@ chol_update_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb,
     }
 }
 
+// ---- trailing update on the FP64 tensor cores (large systems) ---------------------------------
+// Same update, 128x128 tiles, the whole 64-deep panel resident in shared memory (k-major rows of
+// Lt, 16-byte cp.async, rows padded to 132 doubles: conflict-free 8-byte fragment loads), 16 warps
+// each accumulating a 32x32 sub-tile with DMMA.8x8x4, then S -= acc in place.  Per tile 128 KB of
+// L2 reads feed 2.1 MFLOP (the FMA kernel above moves 64 KB per 0.5 MFLOP and is bound by its
+// shared-memory fragment loads: 8 LDS per 16 DFMA).
+__device__ __forceinline__ void upd_cp_async16_zfill(void* smem, const void* gmem, int src_bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void upd_dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int kUT = 128;        // tile edge
+constexpr int kULDS = kUT + 4;  // padded row of the staged panel
+
+__global__ void __launch_bounds__(512)
+chol_update_dmma_kernel(double* __restrict__ S, int ld, int n_rows, int k0,
+                        const double* __restrict__ Lt, const ba_lm_state* ctl, int use_ctl) {
+  if (use_ctl && ctl->done) return;
+  extern __shared__ __align__(16) double dsm[];
+  double* sA = dsm;               // [64][132] rows r0.. of the panel, k-major
+  double* sB = dsm + NB * kULDS;  // [64][132] rows c0.. (unused on diagonal tiles)
+  const int t0 = k0 + NB;
+  int ti = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((ti + 1) * (ti + 2) / 2 <= (int)blockIdx.x) ++ti;
+  while (ti * (ti + 1) / 2 > (int)blockIdx.x) --ti;
+  const int tj = blockIdx.x - ti * (ti + 1) / 2;
+  const bool diag = ti == tj;
+  const int r0 = t0 + ti * kUT, c0 = t0 + tj * kUT;
+  // stage the panel: 64 k-rows x 128 columns per operand = 4096 16-byte pieces, 8 per thread
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int q = threadIdx.x + u * 512;
+    const int m = q >> 6, pc = q & 63;
+    const int ca = r0 + 2 * pc, cb = c0 + 2 * pc;
+    upd_cp_async16_zfill(sA + m * kULDS + 2 * pc, Lt + (size_t)m * ld + (ca < n_rows ? ca : 0), ca < n_rows ? 16 : 0);
+    if (!diag)
+      upd_cp_async16_zfill(sB + m * kULDS + 2 * pc, Lt + (size_t)m * ld + (cb < n_rows ? cb : 0), cb < n_rows ? 16 : 0);
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wr = warp >> 2, wc = warp & 3;
+  const int row0 = wr * 32 + (lane >> 2), col0 = wc * 32 + (lane >> 2);
+  const int kq = lane & 3;
+  // 8-row fragments of this warp that reach below n_rows; on diagonal tiles the sub-tiles
+  // strictly above the diagonal (wc > wr) are skipped altogether
+  int vm = 0, vn = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) vm += (r0 + wr * 32 + 8 * i) < n_rows;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) vn += (c0 + wc * 32 + 8 * j) < n_rows;
+  if (vm == 0 || vn == 0 || (diag && wc > wr)) return;
+  const double* a = sA;
+  const double* b = diag ? sA : sB;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  if (vm == 4 && vn == 4) {
+#pragma unroll 4
+    for (int kk = 0; kk < NB; kk += 4) {
+      double fa[4], fb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) fa[i] = a[(kk + kq) * kULDS + row0 + 8 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) fb[j] = b[(kk + kq) * kULDS + col0 + 8 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) upd_dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+    }
+  } else {
+#pragma unroll 2
+    for (int kk = 0; kk < NB; kk += 4) {
+      double fa[4], fb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) fa[i] = a[(kk + kq) * kULDS + row0 + 8 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) fb[j] = b[(kk + kq) * kULDS + col0 + 8 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (i < vm && j < vn) upd_dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+    }
+  }
+  // S -= acc on the lower triangle; an accumulator pair sits at (row, col), (row, col + 1)
+  const int orow = r0 + wr * 32 + (lane >> 2);
+  const int ocol = c0 + wc * 32 + 2 * (lane & 3);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = orow + 8 * i, c = ocol + 8 * j;
+      if (r >= n_rows || c > r) continue;
+      double* p = S + (size_t)r * ld + c;
+      if (c + 1 <= r) {
+        double2 v = *reinterpret_cast<double2*>(p);
+        v.x -= acc[i][j][0];
+        v.y -= acc[i][j][1];
+        *reinterpret_cast<double2*>(p) = v;
+      } else {
+        *p -= acc[i][j][0];
+      }
+    }
+}
+
 // Back substitution L^T x = y (y = row rhs_row of the factor) by 64-column blocks from the
 // last one: rhs_B = y_B - L[below, B]^T x_below (GEMV), x_B = W_B rhs_B with W_B = L_BB^-T from
 // the panel kernel.  One block; x lives in shared memory.
@@ -282,6 +399,12 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
   constexpr size_t kUpdateSmem = 2 * NB * 65 * sizeof(double);
   BA_CUDA(cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)kUpdateSmem));
+  constexpr size_t kDmmaSmem = 2 * NB * kULDS * sizeof(double);
+  BA_CUDA(cudaFuncSetAttribute(chol_update_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)kDmmaSmem));
+  // 128-tiles need enough of them to fill the GPU; small trailing matrices keep the 64-tile kernel
+  constexpr int kDmmaUpdateMinRows = 2048;
+  static const bool no_dmma_update = std::getenv("BA_CHOL_NO_DMMA") != nullptr;  // A/B timing only
   const int n = e->n_full, n_rows = e->rhs_row + 1, ld = e->n_pad;
   int panel = 0;
   for (int k0 = 0; k0 < n; k0 += NB, ++panel) {
@@ -291,9 +414,16 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
     chol_panel_kernel<<<pblocks, kPanelThreads, kPanelSmem, s>>>(e->P(), ld, n_rows, k0, nb, e->Lt,
                                               e->Winv + (size_t)panel * NB * NB, e->ctl, use_ctl);
     BA_LAUNCH_CHECK();
-    const int nt = below > 0 ? (below + 63) / 64 : 1;
-    dim3 grid(nt, nt);
-    chol_update_kernel<<<grid, 256, kUpdateSmem, s>>>(e->P(), ld, n_rows, k0, nb, e->Lt, e->ctl, use_ctl);
+    if (below <= 0) continue;  // nothing below the last panel
+    if (nb == NB && below >= kDmmaUpdateMinRows && !no_dmma_update) {
+      const int nt = (below + kUT - 1) / kUT;
+      chol_update_dmma_kernel<<<nt * (nt + 1) / 2, 512, kDmmaSmem, s>>>(e->P(), ld, n_rows, k0, e->Lt,
+                                                                       e->ctl, use_ctl);
+    } else {
+      const int nt = (below + 63) / 64;
+      dim3 grid(nt, nt);
+      chol_update_kernel<<<grid, 256, kUpdateSmem, s>>>(e->P(), ld, n_rows, k0, nb, e->Lt, e->ctl, use_ctl);
+    }
     BA_LAUNCH_CHECK();
   }
   const size_t smem = ((size_t)n + 16 * 64 + 64) * sizeof(double);
