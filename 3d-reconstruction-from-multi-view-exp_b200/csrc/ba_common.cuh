@@ -43,6 +43,7 @@ constexpr int kUPart = 54;    // 45 unique entries of U_i + 9 of dF_i
 constexpr int kPT = 12;       // doubles per point in the pair kernel's point table (sparse):
                               // X (3), damped V^-1 (00 01 02 11 12 22), 3 pad = 96 B = 3 sectors
 constexpr int kCholNB = 64;   // panel width of the blocked Cholesky
+constexpr int kCholOB = 256;  // outer block (4 panels) of the two-level variant for large systems
 constexpr int kMaxRecords = 4096;
 constexpr int kMaxRanks = 8;    // ranks of one peer-memory exchange (one NVSwitch domain)
 
@@ -119,7 +120,9 @@ struct ba_engine {
   bool red_in_window = false;  // red lives in the exchange window (freed with it)
   ba::Comm* comm = nullptr;    // non-null: sharded run, sums go through peer memory
   double* Spart = nullptr;  // split-K partial tiles
-  double* Lt = nullptr;     // Cholesky panel, k-major copy [kCholNB][n_pad]
+  double* Lt = nullptr;     // Cholesky block column, k-major copy [kCholOB][n_pad]
+  double* ywork = nullptr;  // [n_pad] running right-hand side of the grid-wide back substitution
+  unsigned int* chol_bar = nullptr;  // grid barrier counter of that kernel
   double* Winv = nullptr;   // [panels][64][64] L_D^-T of every diagonal block (back substitution)
   double* dxi = nullptr;    // [M][9]
   double* cost_part = nullptr;
@@ -226,6 +229,8 @@ int launch_k3(ba_engine* e, bool conditional, cudaStream_t s);
 int syrk_choose_splits(int n_pad, int tile, int64_t k_pad, int num_sms);
 int launch_assemble(ba_engine* e, bool conditional, double c_host, cudaStream_t s);
 int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s);
+int launch_chol_wide_update(double* S, int ld, int n_rows, int t0, const double* Lt, int depth,
+                            const ba_lm_state* ctl, cudaStream_t s);
 int launch_update_trial(ba_engine* e, bool conditional, cudaStream_t s);
 int launch_decide(ba_engine* e, cudaStream_t s);
 int launch_lm_begin(ba_engine* e, double scale, double tol, int max_iter, int max_retries,

@@ -156,7 +156,7 @@ static void free_engine(ba_engine* e) {
   void* ptrs[] = {e->obs_ptr, e->obs_cam, e->obs_pt, e->obs_xy, e->cam_ptr, e->cm_perm, e->bits, e->PT, e->X[0],
                   e->X[1], e->cam[0].f, e->cam[1].f, e->camtab[0], e->camtab[1], e->JP, e->JC, e->V,
                   e->GPT, e->Upart, e->Uloc, e->LINV, e->Z, e->Yt, e->Ysp, e->red_in_window ? nullptr : e->red, e->Spart, e->Lt, e->Winv,
-                  e->dxi, e->cost_part, e->cost_buf, e->ctl, e->rec};
+                  e->dxi, e->cost_part, e->cost_buf, e->ctl, e->rec, e->ywork, e->chol_bar};
   for (void* p : ptrs)
     dev_free(p);
   for (int k = 0; k < 2; ++k) {
@@ -289,7 +289,9 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
   } else {
     A(dev_alloc(&e->Ysp, (size_t)e->nobs * 27));
   }
-  A(dev_alloc(&e->Lt, (size_t)kCholNB * e->n_pad));
+  A(dev_alloc(&e->Lt, (size_t)kCholOB * e->n_pad));
+  A(dev_alloc(&e->ywork, (size_t)e->n_pad));
+  A(dev_alloc(&e->chol_bar, (size_t)4));
   A(dev_alloc(&e->Winv, (size_t)((e->n_full + kCholNB - 1) / kCholNB) * kCholNB * kCholNB));
   A(dev_alloc(&e->dxi, (size_t)e->n_full));
   A(dev_alloc(&e->cost_part, (size_t)e->num_sms * 16 + 1024));

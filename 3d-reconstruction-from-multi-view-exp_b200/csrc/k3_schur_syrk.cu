@@ -48,11 +48,15 @@ __device__ __forceinline__ void tile_from_linear(int t, int& ti, int& tj) {
 }
 
 // TILE x TILE output tile per CTA; WR x WC warps, each owning a (TILE/WR) x (TILE/WC) sub-tile.
-template <int TILE, int WR, int WC, int KC>
+// SUB = false: the tile of this split is written to part[split][tile] (Schur product).
+// SUB = true:  one split; the tile is subtracted in place from the lower triangle of the n_store x
+//              n_store matrix `part` (leading dimension ld) -- the rank-k trailing update of the
+//              blocked Cholesky (k4_cholesky.cu), where Yt is the k-major copy of a block column.
+template <int TILE, int WR, int WC, int KC, bool SUB>
 __global__ void __launch_bounds__(WR* WC * 32)
 syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_chunks,
                  int chunks_per_split, int n_tiles, double* __restrict__ part,
-                 const ba_lm_state* ctl) {
+                 const ba_lm_state* ctl, int n_store) {
   if (ctl && ctl->done) return;
   constexpr int NT = WR * WC * 32;
   constexpr int LDS = TILE + 4;
@@ -169,10 +173,30 @@ syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_c
   }
   cp_async_wait<0>();
 
-  // partial tile [split][tile][TILE][TILE]
-  double* out = part + ((size_t)split * n_tiles + t) * TILE * TILE;
   const int orow = wr * WM + (lane >> 2);
   const int ocol = wc * WN + 2 * (lane & 3);
+  if (SUB) {
+    // S -= acc on the lower triangle; an accumulator pair sits at (r, c), (r, c + 1), c even
+#pragma unroll
+    for (int i = 0; i < FM; ++i)
+#pragma unroll
+      for (int j = 0; j < FN; ++j) {
+        const int r = ti * TILE + orow + 8 * i, c = tj * TILE + ocol + 8 * j;
+        if (r >= n_store || c > r) continue;
+        double* p = part + (size_t)r * ld + c;
+        if (c + 1 <= r) {
+          double2 v = *reinterpret_cast<double2*>(p);
+          v.x -= acc[i][j][0];
+          v.y -= acc[i][j][1];
+          *reinterpret_cast<double2*>(p) = v;
+        } else {
+          *p -= acc[i][j][0];
+        }
+      }
+    return;
+  }
+  // partial tile [split][tile][TILE][TILE]
+  double* out = part + ((size_t)split * n_tiles + t) * TILE * TILE;
 #pragma unroll
   for (int i = 0; i < FM; ++i)
 #pragma unroll
@@ -271,13 +295,13 @@ static int launch_syrk(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
   const int splits = e->syrk_splits;
   const int cps = (int)((n_chunks + splits - 1) / splits);
   const size_t smem = (size_t)2 * kStages * KC * (TILE + 4) * sizeof(double);
-  BA_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<TILE, WR, WC, KC>,
+  BA_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<TILE, WR, WC, KC, false>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(n_tiles, splits);
   {
     ProfScope ps(e, PG_SYRK, s);
-    syrk_dmma_kernel<TILE, WR, WC, KC><<<grid, WR * WC * 32, smem, s>>>(
-        e->Yt, e->n_pad, e->n_pad, n_chunks, cps, n_tiles, e->Spart, ctl);
+    syrk_dmma_kernel<TILE, WR, WC, KC, false><<<grid, WR * WC * 32, smem, s>>>(
+        e->Yt, e->n_pad, e->n_pad, n_chunks, cps, n_tiles, e->Spart, ctl, 0);
     BA_LAUNCH_CHECK();
   }
   const int slabs = n_tiles >= 4 * e->num_sms ? 1 : (n_tiles >= e->num_sms ? 4 : 8);
@@ -285,6 +309,32 @@ static int launch_syrk(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
                                                                e->n_pad, e->n_pad, ctl);
   BA_LAUNCH_CHECK();
   return BA_OK;
+}
+
+// S[t0:, t0:] -= Lt[:, t0:]^T Lt[:, t0:]  (lower triangle, rows < n_rows) with Lt k-major
+// [depth][ld]: the wide trailing update of the two-level blocked Cholesky.
+template <int TILE, int WR, int WC, int KC>
+static int launch_syrk_sub(double* S, int ld, int n_rows, int t0, const double* Lt, int depth,
+                           const ba_lm_state* ctl, cudaStream_t s) {
+  const int n_store = n_rows - t0;
+  const int n_valid = (n_store + 7) / 8 * 8;  // <= ld - t0: ld is a multiple of 8, t0 of 64
+  const int nt1 = (n_valid + TILE - 1) / TILE;
+  const int n_tiles = nt1 * (nt1 + 1) / 2;
+  const int n_chunks = depth / KC;
+  const size_t smem = (size_t)2 * kStages * KC * (TILE + 4) * sizeof(double);
+  BA_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<TILE, WR, WC, KC, true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  syrk_dmma_kernel<TILE, WR, WC, KC, true><<<dim3(n_tiles, 1), WR * WC * 32, smem, s>>>(
+      Lt + t0, ld, n_valid, n_chunks, n_chunks, n_tiles, S + (size_t)t0 * ld + t0, ctl, n_store);
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}
+
+int launch_chol_wide_update(double* S, int ld, int n_rows, int t0, const double* Lt, int depth,
+                            const ba_lm_state* ctl, cudaStream_t s) {
+  // 128-tiles (one CTA per SM) once there are enough of them, 64-tiles (four per SM) below
+  if (n_rows - t0 >= 2560) return launch_syrk_sub<128, 4, 4, 32>(S, ld, n_rows, t0, Lt, depth, ctl, s);
+  return launch_syrk_sub<64, 2, 2, 16>(S, ld, n_rows, t0, Lt, depth, ctl, s);
 }
 
 int launch_k3(ba_engine* e, bool conditional, cudaStream_t s) {

@@ -152,10 +152,13 @@ chol_panel_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb,
 }
 
 // Trailing update S[r][c] -= sum_m L[r][k0+m] L[c][k0+m] on 64x64 tiles of the lower triangle
-// (rows/cols >= k0+nb, rows < n_rows).  The diagonal blocks of S keep their pre-factor content:
-// nothing reads L_D from S afterwards (the back substitution uses W = L_D^-T).
+// (rows >= cols >= k0+nb, rows < n_rows, cols < c_end).  The diagonal blocks of S keep their
+// pre-factor content: nothing reads L_D from S afterwards (the back substitution uses W = L_D^-T).
+// Small systems: c_end = n_rows, the whole trailing matrix after every panel.  Large systems
+// (two-level blocking): only the columns of the current 256-wide outer block; the rest of the
+// trailing matrix waits for the rank-256 update on the tensor cores (launch_chol_wide_update).
 __global__ void __launch_bounds__(256)
-chol_update_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb,
+chol_update_kernel(double* __restrict__ S, int ld, int n_rows, int c_end, int k0, int nb,
                    const double* __restrict__ Lt, const ba_lm_state* ctl, int use_ctl) {
   if (use_ctl && ctl->done) return;
   const int tid = threadIdx.x;
@@ -163,7 +166,7 @@ chol_update_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb,
   const int ti = blockIdx.y, tj = blockIdx.x;
   if (tj > ti) return;
   const int r0 = t0 + ti * 64, c0 = t0 + tj * 64;
-  if (r0 >= n_rows) return;
+  if (r0 >= n_rows || c0 >= c_end) return;
   constexpr int MH = NB;  // the whole panel depth in one pass: all loads in flight at once
   extern __shared__ double usm[];
   double(*sA)[64 + 1] = reinterpret_cast<double(*)[64 + 1]>(usm);
@@ -210,122 +213,7 @@ chol_update_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb,
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int r = r0 + ty + 16 * i, c = c0 + tx + 16 * j;
-      if (r < n_rows && c <= r) S[(size_t)r * ld + c] -= acc[i][j];
-    }
-}
-
-// ---- trailing update on the FP64 tensor cores (large systems) ---------------------------------
-// Same update, 128x128 tiles, the whole 64-deep panel resident in shared memory (k-major rows of
-// Lt, 16-byte cp.async, rows padded to 132 doubles: conflict-free 8-byte fragment loads), 16 warps
-// each accumulating a 32x32 sub-tile with DMMA.8x8x4, then S -= acc in place.  Per tile 128 KB of
-// L2 reads feed 2.1 MFLOP (the FMA kernel above moves 64 KB per 0.5 MFLOP and is bound by its
-// shared-memory fragment loads: 8 LDS per 16 DFMA).
-__device__ __forceinline__ void upd_cp_async16_zfill(void* smem, const void* gmem, int src_bytes) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
-}
-__device__ __forceinline__ void upd_dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-
-constexpr int kUT = 128;        // tile edge
-constexpr int kULDS = kUT + 4;  // padded row of the staged panel
-
-__global__ void __launch_bounds__(512)
-chol_update_dmma_kernel(double* __restrict__ S, int ld, int n_rows, int k0,
-                        const double* __restrict__ Lt, const ba_lm_state* ctl, int use_ctl) {
-  if (use_ctl && ctl->done) return;
-  extern __shared__ __align__(16) double dsm[];
-  double* sA = dsm;               // [64][132] rows r0.. of the panel, k-major
-  double* sB = dsm + NB * kULDS;  // [64][132] rows c0.. (unused on diagonal tiles)
-  const int t0 = k0 + NB;
-  int ti = (int)((sqrt(8.0 * blockIdx.x + 1.0) - 1.0) * 0.5);
-  while ((ti + 1) * (ti + 2) / 2 <= (int)blockIdx.x) ++ti;
-  while (ti * (ti + 1) / 2 > (int)blockIdx.x) --ti;
-  const int tj = blockIdx.x - ti * (ti + 1) / 2;
-  const bool diag = ti == tj;
-  const int r0 = t0 + ti * kUT, c0 = t0 + tj * kUT;
-  // stage the panel: 64 k-rows x 128 columns per operand = 4096 16-byte pieces, 8 per thread
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int q = threadIdx.x + u * 512;
-    const int m = q >> 6, pc = q & 63;
-    const int ca = r0 + 2 * pc, cb = c0 + 2 * pc;
-    upd_cp_async16_zfill(sA + m * kULDS + 2 * pc, Lt + (size_t)m * ld + (ca < n_rows ? ca : 0), ca < n_rows ? 16 : 0);
-    if (!diag)
-      upd_cp_async16_zfill(sB + m * kULDS + 2 * pc, Lt + (size_t)m * ld + (cb < n_rows ? cb : 0), cb < n_rows ? 16 : 0);
-  }
-  asm volatile("cp.async.commit_group;\n" ::);
-  asm volatile("cp.async.wait_group 0;\n" ::);
-  __syncthreads();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wr = warp >> 2, wc = warp & 3;
-  const int row0 = wr * 32 + (lane >> 2), col0 = wc * 32 + (lane >> 2);
-  const int kq = lane & 3;
-  // 8-row fragments of this warp that reach below n_rows; on diagonal tiles the sub-tiles
-  // strictly above the diagonal (wc > wr) are skipped altogether
-  int vm = 0, vn = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) vm += (r0 + wr * 32 + 8 * i) < n_rows;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) vn += (c0 + wc * 32 + 8 * j) < n_rows;
-  if (vm == 0 || vn == 0 || (diag && wc > wr)) return;
-  const double* a = sA;
-  const double* b = diag ? sA : sB;
-  double acc[4][4][2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  if (vm == 4 && vn == 4) {
-#pragma unroll 4
-    for (int kk = 0; kk < NB; kk += 4) {
-      double fa[4], fb[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) fa[i] = a[(kk + kq) * kULDS + row0 + 8 * i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) fb[j] = b[(kk + kq) * kULDS + col0 + 8 * j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) upd_dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-    }
-  } else {
-#pragma unroll 2
-    for (int kk = 0; kk < NB; kk += 4) {
-      double fa[4], fb[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) fa[i] = a[(kk + kq) * kULDS + row0 + 8 * i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) fb[j] = b[(kk + kq) * kULDS + col0 + 8 * j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (i < vm && j < vn) upd_dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-    }
-  }
-  // S -= acc on the lower triangle; an accumulator pair sits at (row, col), (row, col + 1)
-  const int orow = r0 + wr * 32 + (lane >> 2);
-  const int ocol = c0 + wc * 32 + 2 * (lane & 3);
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = orow + 8 * i, c = ocol + 8 * j;
-      if (r >= n_rows || c > r) continue;
-      double* p = S + (size_t)r * ld + c;
-      if (c + 1 <= r) {
-        double2 v = *reinterpret_cast<double2*>(p);
-        v.x -= acc[i][j][0];
-        v.y -= acc[i][j][1];
-        *reinterpret_cast<double2*>(p) = v;
-      } else {
-        *p -= acc[i][j][0];
-      }
+      if (r < n_rows && c <= r && c < c_end) S[(size_t)r * ld + c] -= acc[i][j];
     }
 }
 
@@ -391,6 +279,94 @@ chol_backsolve_kernel(const double* __restrict__ S, int ld, int n, int rhs_row,
   for (int k = tid; k < n; k += 1024) dxi[k] = x[k];
 }
 
+// The same back substitution for large systems, spread over the GPU (the single-block kernel
+// above streams n^2/2 doubles through one SM: 4.6 ms at n = 9000).  Right-looking: once x_B of a
+// 64-block is known, y[c] -= sum_{r in B} L[r][c] x_B[r] for all columns c before B.  Columns are
+// dealt to the CTAs in chunks of 64; after a grid barrier every CTA forms the next x_B itself
+// (x_B = W_B y_B, 64x64, redundantly: no second barrier), the owner of the chunk stores it, and
+// all CTAs update their own chunks.  The rows L[B][.] a CTA needs for its next update do not
+// depend on x, so they are fetched BEFORE the barrier and the HBM latency overlaps the wait.
+// One barrier per block; fixed summation order (deterministic).  All CTAs must be co-resident:
+// the grid never exceeds the SM count and the kernel runs alone on its stream.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+chol_backsolve_grid_kernel(const double* __restrict__ S, int ld, int n, int rhs_row,
+                           const double* __restrict__ W, double* __restrict__ ywork,
+                           double* __restrict__ dxi, unsigned int* bar, const ba_lm_state* ctl,
+                           int use_ctl) {
+  if (use_ctl && ctl->done) return;
+  __shared__ double xB[NB], yB[NB], part[4][NB];
+  const int tid = threadIdx.x, G = gridDim.x, cta = blockIdx.x;
+  const int col = tid & 63, rg = tid >> 6;  // update: 64 columns x 4 groups of 16 rows
+  const int nblk = (n + NB - 1) / NB;
+  // running rhs of the chunks this CTA owns (chunk q belongs to CTA q % G)
+  for (int q = cta; q < nblk; q += G)
+    if (tid < NB && q * NB + tid < n) ywork[q * NB + tid] = S[(size_t)rhs_row * ld + q * NB + tid];
+  // rows of block `blk` restricted to chunk q: 16 values per thread, fetched one step ahead
+  double pre[16];
+  auto prefetch = [&](int blk, int q) {
+    const int b0 = blk * NB;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int r = b0 + rg * 16 + u;
+      pre[u] = (q < blk && r < n) ? S[(size_t)r * ld + q * NB + col] : 0.0;
+    }
+  };
+  prefetch(nblk - 1, cta);
+  unsigned int epoch = 0;
+  grid_barrier(bar, ++epoch * G);
+  for (int blk = nblk - 1; blk >= 0; --blk) {
+    const int b0 = blk * NB;
+    const int w = n - b0 < NB ? n - b0 : NB;
+    if (tid < NB) yB[tid] = tid < w ? __ldcg(ywork + b0 + tid) : 0.0;
+    __syncthreads();
+    {
+      const int j = tid >> 2, p4 = tid & 3;  // x_B[j] = sum_c W[j][c] y_B[c]
+      const double* Wj = W + (size_t)blk * NB * NB + (size_t)j * NB + p4 * 16;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int c = 0; c < 16; c += 2) {
+        a0 = fma(Wj[c], yB[p4 * 16 + c], a0);
+        a1 = fma(Wj[c + 1], yB[p4 * 16 + c + 1], a1);
+      }
+      double sx = a0 + a1;
+      sx += __shfl_xor_sync(0xffffffffu, sx, 1);
+      sx += __shfl_xor_sync(0xffffffffu, sx, 2);
+      if (p4 == 0) {
+        xB[j] = sx;
+        if (blk % G == cta && j < w) dxi[b0 + j] = sx;
+      }
+    }
+    __syncthreads();
+    // chunks of this CTA below the block (with G >= nblk, the usual case, exactly one)
+    for (int q = cta; q < blk; q += G) {
+      double acc = 0.0;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) acc = fma(pre[u], xB[rg * 16 + u], acc);
+      if (q + G < blk) prefetch(blk, q + G);
+      part[rg][col] = acc;
+      __syncthreads();
+      if (rg == 0 && q * NB + col < n)
+        ywork[q * NB + col] -= (part[0][col] + part[1][col]) + (part[2][col] + part[3][col]);
+      __syncthreads();
+    }
+    if (blk > 0) prefetch(blk - 1, cta);  // static data: in flight while the barrier is awaited
+    if (blk > 0) grid_barrier(bar, ++epoch * G);
+  }
+}
+
 int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
   const int use_ctl = conditional ? 1 : 0;
   constexpr size_t kPanelSmem = (2 * NB * (NB + 1) + 5 * NB) * sizeof(double);
@@ -399,32 +375,42 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
   constexpr size_t kUpdateSmem = 2 * NB * 65 * sizeof(double);
   BA_CUDA(cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)kUpdateSmem));
-  constexpr size_t kDmmaSmem = 2 * NB * kULDS * sizeof(double);
-  BA_CUDA(cudaFuncSetAttribute(chol_update_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)kDmmaSmem));
-  // 128-tiles need enough of them to fill the GPU; small trailing matrices keep the 64-tile kernel
-  constexpr int kDmmaUpdateMinRows = 2048;
-  static const bool no_dmma_update = std::getenv("BA_CHOL_NO_DMMA") != nullptr;  // A/B timing only
   const int n = e->n_full, n_rows = e->rhs_row + 1, ld = e->n_pad;
+  // Small systems: after every 64-panel the whole trailing matrix is updated (FMA 64-tiles).
+  // Large systems: two-level blocking.  Inside a 256-wide outer block the panels update only the
+  // block's own columns; the rest of the trailing matrix then gets ONE rank-256 update on the
+  // FP64 tensor cores (the SYRK kernel of K3 with a subtracting epilogue), which reads and writes
+  // S a quarter as often and keeps the DMMA pipe fed from a 3-stage cp.async pipeline.
+  static const bool one_level = std::getenv("BA_CHOL_ONE_LEVEL") != nullptr;  // A/B timing only
+  const int OB = (n_rows >= 2048 && !one_level) ? kCholOB : NB;
   int panel = 0;
-  for (int k0 = 0; k0 < n; k0 += NB, ++panel) {
-    const int nb = n - k0 < NB ? n - k0 : NB;
-    const int below = n_rows - (k0 + nb);
-    const int pblocks = 1 + (below + NB - 1) / NB;
-    chol_panel_kernel<<<pblocks, kPanelThreads, kPanelSmem, s>>>(e->P(), ld, n_rows, k0, nb, e->Lt,
-                                              e->Winv + (size_t)panel * NB * NB, e->ctl, use_ctl);
-    BA_LAUNCH_CHECK();
-    if (below <= 0) continue;  // nothing below the last panel
-    if (nb == NB && below >= kDmmaUpdateMinRows && !no_dmma_update) {
-      const int nt = (below + kUT - 1) / kUT;
-      chol_update_dmma_kernel<<<nt * (nt + 1) / 2, 512, kDmmaSmem, s>>>(e->P(), ld, n_rows, k0, e->Lt,
-                                                                       e->ctl, use_ctl);
-    } else {
-      const int nt = (below + 63) / 64;
-      dim3 grid(nt, nt);
-      chol_update_kernel<<<grid, 256, kUpdateSmem, s>>>(e->P(), ld, n_rows, k0, nb, e->Lt, e->ctl, use_ctl);
+  for (int K0 = 0; K0 < n; K0 += OB) {
+    // columns the panels of this block update themselves
+    const int c_end = (OB == NB || K0 + OB > n_rows) ? n_rows : K0 + OB;
+    for (int k0 = K0; k0 < K0 + OB && k0 < n; k0 += NB, ++panel) {
+      const int nb = n - k0 < NB ? n - k0 : NB;
+      const int below = n_rows - (k0 + nb);
+      const int pblocks = 1 + (below + NB - 1) / NB;
+      double* Lt = e->Lt + (size_t)(k0 - K0) * ld;  // k-rows of this panel inside the block column
+      chol_panel_kernel<<<pblocks, kPanelThreads, kPanelSmem, s>>>(e->P(), ld, n_rows, k0, nb, Lt,
+                                                e->Winv + (size_t)panel * NB * NB, e->ctl, use_ctl);
+      BA_LAUNCH_CHECK();
+      if (below <= 0 || k0 + nb >= c_end) continue;
+      dim3 grid((c_end - (k0 + nb) + 63) / 64, (below + 63) / 64);
+      chol_update_kernel<<<grid, 256, kUpdateSmem, s>>>(e->P(), ld, n_rows, c_end, k0, nb, Lt, e->ctl, use_ctl);
+      BA_LAUNCH_CHECK();
     }
+    if (OB > NB && K0 + OB < n_rows)  // all four panels of the block are full here
+      BA_TRY(launch_chol_wide_update(e->P(), ld, n_rows, K0 + OB, e->Lt, OB, e->ctl, s));
+  }
+  if (n >= 2048 && !std::getenv("BA_CHOL_BACKSOLVE_1CTA")) {
+    const int nblk = (n + NB - 1) / NB;
+    const int G = nblk < e->num_sms ? nblk : e->num_sms;
+    BA_CUDA(cudaMemsetAsync(e->chol_bar, 0, sizeof(unsigned int), s));
+    chol_backsolve_grid_kernel<<<G, 256, 0, s>>>(e->P(), ld, n, e->rhs_row, e->Winv, e->ywork, e->dxi,
+                                                 e->chol_bar, e->ctl, use_ctl);
     BA_LAUNCH_CHECK();
+    return BA_OK;
   }
   const size_t smem = ((size_t)n + 16 * 64 + 64) * sizeof(double);
   if (smem > 220 * 1024) {

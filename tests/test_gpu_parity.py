@@ -131,8 +131,8 @@ def test_kernels_match_oracle_on_golden_cases(ba, name):
     (70, 3000, 0.9, "x-up_z-forward"),      # sparse path, nearly full bitmaps: multi-pass hit queue, 3 x 3 pair tiles
     (33, 200, 0.5, "x-right_z-forward"),    # sparse path, one camera beyond a pair tile, single bitmap batch
     (5, 9000, 0.7, "x-up_z-forward"),       # sparse path, few cameras, several bitmap batches per pair
-    (300, 500, 0.3, "x-up_z-forward"),      # n = 2700: Cholesky trailing update on DMMA 128-tiles (>= 2048 rows below)
-    (260, 300, 1.0, "x-right_z-forward"),   # n = 2340, dense: same, edge tiles of the update cut by n_rows
+    (320, 450, 0.3, "x-up_z-forward"),      # n = 2880: two-level Cholesky (rank-256 DMMA updates, 128- and 64-tiles), grid-wide back substitution
+    (260, 300, 1.0, "x-right_z-forward"),   # n = 2340, dense: same with 64-tiles only, edge tiles cut by n_rows
 ])
 def test_kernels_match_oracle_on_random_scenes(ba, n_cams, n_points, visibility, axis):
     sc = ba.scenes.make_scene(n_cams, n_points, seed=n_cams, visibility=visibility, axis=axis)
