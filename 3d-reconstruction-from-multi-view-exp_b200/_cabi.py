@@ -56,6 +56,8 @@ SIGNATURES = {
     "ba_set_observations": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
     "ba_set_state": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "ba_get_state": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "ba_set_state_global": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "ba_get_state_global": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, _P]),
     "ba_cost": (C.c_int, [_P, C.c_int, _P]),
     "ba_linearize": (C.c_int, [_P, _P]),
     "ba_build_reduced": (C.c_int, [_P, C.c_double, _P]),

@@ -10,7 +10,9 @@ Additions that the reference does not have (all keyword-only / separate construc
     (``exchange="peer"`` whenever the group runs on NCCL, i.e. one GPU per rank) by the
     library's own kernels over NVLink peer memory, otherwise (``exchange="collective"``) by
     two ``torch.distributed`` all-reduces;
-  * ``max_retries`` -- a cap on inner solves per iteration (the reference loops forever, :118).
+  * ``max_retries`` -- a cap on inner solves per iteration (the reference loops forever, :118);
+  * ``gauge_on_device`` -- the O(N) gauge normalisation / de-normalisation passes (:208-258) run
+    as CUDA kernels (``ba_set_state_global`` / ``ba_get_state_global``) instead of NumPy.
 """
 from __future__ import annotations
 
@@ -59,7 +61,7 @@ class BundleAdjuster:
     def __init__(self, x, init_X, init_K, init_R, init_t, f0=1.0, visibility_index=None,
                  axis="x-right_z-forward", *, observations: ObservationList | None = None,
                  device: int | None = None, process_group=None, max_retries: int = 200,
-                 exchange: str = "auto"):
+                 exchange: str = "auto", gauge_on_device: bool = False):
         gauge.axis_component(axis)  # ValueError() for an unknown axis (:28)
         init_X = np.asarray(init_X, dtype=np.float64)
         init_R = np.asarray(init_R, dtype=np.float64)
@@ -82,7 +84,11 @@ class BundleAdjuster:
             raise ValueError("observations do not match init_X / init_R")
 
         # normalised frame (:40-42); intrinsics (:45-48) as fresh arrays
-        self._X, self._R, self._t = gauge.normalize(init_X, init_R, init_t, axis)
+        self._gauge_on_device = bool(gauge_on_device)
+        if self._gauge_on_device:
+            self._X = self._R = self._t = None  # the normalised state exists on the device only
+        else:
+            self._X, self._R, self._t = gauge.normalize(init_X, init_R, init_t, axis)
         self._f = np.array(init_K[:, 0, 0], dtype=np.float64)
         self._u = np.array(init_K[:, :2, 2], dtype=np.float64)
 
@@ -95,7 +101,10 @@ class BundleAdjuster:
             device = _default_device()
         self._engine = Engine(self._n_points, self._n_images, obs.n_obs, self._f0, axis, obs.dense, device)
         self._engine.set_observations(obs.obs_ptr, obs.obs_cam, obs.obs_xy)
-        self._engine.set_state(self._X, self._R, self._t, self._f, self._u)
+        if self._gauge_on_device:
+            self._engine.set_state_global(init_X, init_R, init_t, self._f, self._u)
+        else:
+            self._engine.set_state(self._X, self._R, self._t, self._f, self._u)
         self._peer_exchange = False
         self._quiet = False  # sharded runs: only rank 0 prints the iteration lines (:188)
         if exchange not in ("auto", "peer", "collective"):
@@ -146,6 +155,8 @@ class BundleAdjuster:
             for r in recs:
                 self._record(r.E_prev, r.E, r.delta, r.c, r.solves, r.count)
 
+        if self._gauge_on_device:
+            return eng.get_state_global(0)  # (:198-202) on the device
         self._X, self._R, self._t, self._f, self._u = eng.get_state(0)
         # back to the caller's frame (:198-200)
         self._X, self._R, self._t = gauge.denormalize(self._R0, self._t0, self._c0c1_len,

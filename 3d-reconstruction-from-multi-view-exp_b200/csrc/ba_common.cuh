@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "ba_b200.h"
 
@@ -72,6 +73,14 @@ struct ProfSlot {
   int64_t launches = 0;
 };
 
+// A timed scope whose events have been recorded but not read yet: reading them needs a host
+// synchronisation, and a synchronisation after every scope would let the GPU drain between
+// kernels (launch latency inside the brackets).  They are resolved when the profile is read.
+struct ProfPending {
+  int group;
+  cudaEvent_t a, b;
+};
+
 }  // namespace ba
 
 // The opaque engine of the C ABI.
@@ -103,6 +112,8 @@ struct ba_engine {
   double* X[2] = {nullptr, nullptr};
   ba::CamState cam[2];
   double* camtab[2] = {nullptr, nullptr};
+  double* gauge = nullptr;  // [16] R0, t0, divisor s, baseline length (k6_gauge.cu)
+  bool have_gauge = false;
 
   // linearisation
   double *JP = nullptr, *JC = nullptr, *V = nullptr, *GPT = nullptr;
@@ -143,6 +154,7 @@ struct ba_engine {
   // profiling
   bool profiling = false;
   ba::ProfSlot prof[ba::PG_COUNT];
+  std::vector<ba::ProfPending> prof_pending;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
   double* P() const { return red; }
@@ -173,15 +185,24 @@ struct ProfScope {
     e->prof[group].launches += g_launch_count - launches_before;
     if (a) {
       cudaEventRecord(b, s);
-      cudaEventSynchronize(b);
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, a, b);
-      e->prof[group].ms += ms;
-      cudaEventDestroy(a);
-      cudaEventDestroy(b);
+      e->prof_pending.push_back({group, a, b});
     }
   }
 };
+
+// Read the recorded scopes (synchronises on their events) into the per-group totals.
+inline void prof_resolve(ba_engine* e, bool keep) {
+  for (const ProfPending& p : e->prof_pending) {
+    if (keep) {
+      cudaEventSynchronize(p.b);
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) e->prof[p.group].ms += ms;
+    }
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  e->prof_pending.clear();
+}
 
 #define BA_LAUNCH_CHECK()                                                       \
   do {                                                                          \

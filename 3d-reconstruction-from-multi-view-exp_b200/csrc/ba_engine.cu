@@ -152,11 +152,12 @@ static void free_engine(ba_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+  prof_resolve(e, false);
   comm_free(e);  // closes the peers' windows and frees this rank's (which holds red)
   void* ptrs[] = {e->obs_ptr, e->obs_cam, e->obs_pt, e->obs_xy, e->cam_ptr, e->cm_perm, e->bits, e->PT, e->X[0],
                   e->X[1], e->cam[0].f, e->cam[1].f, e->camtab[0], e->camtab[1], e->JP, e->JC, e->V,
                   e->GPT, e->Upart, e->Uloc, e->LINV, e->Z, e->Yt, e->Ysp, e->red_in_window ? nullptr : e->red, e->Spart, e->Lt, e->Winv,
-                  e->dxi, e->cost_part, e->cost_buf, e->ctl, e->rec, e->ywork, e->chol_bar};
+                  e->dxi, e->cost_part, e->cost_buf, e->ctl, e->rec, e->ywork, e->chol_bar, e->gauge};
   for (void* p : ptrs)
     dev_free(p);
   for (int k = 0; k < 2; ++k) {
@@ -272,6 +273,7 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
     A(alloc_cam(&e->cam[w], e->M));
     A(dev_alloc(&e->camtab[w], (size_t)e->M * kCamTab));
   }
+  A(dev_alloc(&e->gauge, (size_t)16));
   A(dev_alloc(&e->JP, (size_t)e->nobs * kJP));
   A(dev_alloc(&e->JC, (size_t)e->nobs * kJC));
   A(dev_alloc(&e->V, (size_t)6 * e->N));
@@ -751,6 +753,7 @@ static int group_id(const char* g) {
 int ba_profile_get(ba_engine* e, const char* group, double* total_ms, int64_t* launches) {
   const int g = group_id(group);
   if (!e || g < 0) { set_error("unknown profile group"); return BA_ERR_INVALID; }
+  prof_resolve(e, true);
   if (total_ms) *total_ms = e->prof[g].ms;
   if (launches) *launches = e->prof[g].launches;
   return BA_OK;
@@ -758,6 +761,7 @@ int ba_profile_get(ba_engine* e, const char* group, double* total_ms, int64_t* l
 
 int ba_profile_reset(ba_engine* e) {
   if (!e) { set_error("null engine"); return BA_ERR_INVALID; }
+  prof_resolve(e, false);
   for (int i = 0; i < PG_COUNT; ++i) e->prof[i] = ProfSlot();
   return BA_OK;
 }

@@ -121,6 +121,9 @@ syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_c
   for (int i = 0; i < FM; ++i) vm += (ti * TILE + wr * WM + 8 * i) < n_valid;
 #pragma unroll
   for (int j = 0; j < FN; ++j) vn += (tj * TILE + wc * WN + 8 * j) < n_valid;
+  // on a diagonal tile the warps whose sub-tile lies strictly above the diagonal have nothing to
+  // compute (nothing above the diagonal is read anywhere): they only help with the copies
+  if (diag && WM == WN && wc > wr) vm = 0;
   const bool full = vm == FM && vn == FN;
 
   double acc[FM][FN][2];

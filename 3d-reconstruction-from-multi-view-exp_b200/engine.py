@@ -122,6 +122,26 @@ class Engine:
                                            f.ctypes.data, u.ctypes.data, _cabi.BA_MEM_HOST, self.stream))
         return X, R, t, f, u
 
+    def set_state_global(self, X, R, t, f, u):
+        """State in the caller's frame; the gauge normalisation (:208-240) runs on the device."""
+        ptrs, mems, keep = [], set(), []
+        for a in (X, R, t, f, u):
+            p, m, k = _ptr(a, np.float64)
+            ptrs.append(p)
+            keep.append(k)
+            mems.add(m)
+        if len(mems) > 1:
+            raise ValueError("state arrays must all be host arrays or all be device tensors")
+        _cabi.check(self._lib.ba_set_state_global(self._h, *ptrs, mems.pop(), self.stream))
+
+    def get_state_global(self, which: int = 0):
+        """(X, K, R, t) back in the caller's frame (:242-258, :283-289), transformed on the device."""
+        N, M = self.n_points, self.n_cams
+        X, K, R, t = np.empty((N, 3)), np.empty((M, 3, 3)), np.empty((M, 3, 3)), np.empty((M, 3))
+        _cabi.check(self._lib.ba_get_state_global(self._h, which, X.ctypes.data, K.ctypes.data, R.ctypes.data,
+                                                  t.ctypes.data, _cabi.BA_MEM_HOST, self.stream))
+        return X, K, R, t
+
     # -- single phases ------------------------------------------------------------------------
     def cost(self, which: int = 0) -> float:
         _cabi.check(self._lib.ba_cost(self._h, which, self.stream))

@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "collective"],
                     help="N > 1: how the ranks sum the partial reduced system and the cost: the library's "
                          "own kernels over NVLink peer memory (auto/peer) or torch.distributed all-reduces")
+    ap.add_argument("--profile-ranks", action="store_true",
+                    help="N > 1: re-run the K iterations with per-phase CUDA-event timing on every rank "
+                         "(eager launches) and add rank 0's phase table; `comm` includes waiting for peers")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: the named scene's points are split over the ranks "
                          "(default: weak, every rank owns a full named scene)")
@@ -218,10 +221,11 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     h_cam = None if sc.dense else pinned(sc.obs_cam)
     h_X0, h_K0, h_R0, h_t0 = pinned(sc.X0), pinned(sc.K0), pinned(sc.R0), pinned(sc.t0)
 
-    def make_adjuster():
+    def make_adjuster(gauge_on_device=False):
         return ba_b200.BundleAdjuster.from_observations(
             h_ptr, h_cam, h_xy, h_X0, h_K0, h_R0, h_t0, f0=sc.f0, axis=sc.axis, dense=sc.dense,
-            device=local_rank, process_group=group, exchange=args.exchange)
+            device=local_rank, process_group=group, exchange=args.exchange,
+            gauge_on_device=gauge_on_device)
 
     def barrier():
         if dist is not None:
@@ -333,6 +337,18 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
                              "peak_source": "MEASURED_PEAKS.json" if hbm else "fallback",
                              "frac": gbs / (hbm or 6650.0), "bytes_per_obs": 240}
 
+    if world > 1 and args.profile_ranks and adj._peer_exchange:
+        eng = adj.engine
+        eng.profile_enable(True)
+        eng.profile_reset()
+        barrier()
+        run_iters(adj, K)
+        prof = eng.profile()
+        eng.profile_enable(False)
+        barrier()
+        if rank == 0:
+            out["phase_ms_per_step"] = {k: v["ms"] / K for k, v in prof.items()}
+
     # the device-resident engine is released first: the end-to-end arm re-creates one, as a
     # caller that adjusts scene after scene would
     adj.engine.close()
@@ -346,7 +362,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     for _ in range(E2E_REPS):
         barrier()
         t0 = time.perf_counter()
-        adj2 = make_adjuster()
+        adj2 = make_adjuster(gauge_on_device=True)
         with contextlib.redirect_stdout(io.StringIO()):
             Xr, Kr, Rr, tr = adj2.optimize(SCALE, TOL_NEVER, max_iter=K)
         torch.cuda.synchronize()

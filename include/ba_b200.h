@@ -112,6 +112,16 @@ int ba_set_state(ba_engine* e, const double* X, const double* R, const double* t
                  const double* f, const double* u, int mem, void* stream);
 int ba_get_state(ba_engine* e, int which, double* X, double* R, double* t, double* f, double* u,
                  int mem, void* stream);
+/* The same in the CALLER's frame, with the gauge handled on the device:
+ * ba_set_state_global takes init_X / init_R / init_t as the constructor receives them (:11-21),
+ * keeps camera 0's pose and the baseline length (:23-33) and stores the normalised state
+ * (_transform_to_normalize_coodinates, :208-240, incl. its signed divisor);
+ * ba_get_state_global returns state `which` transformed back (:242-258) with K assembled
+ * from f, u, f0 (:283-289): X[n_points][3], K[n_cams][3][3], R[n_cams][3][3], t[n_cams][3]. */
+int ba_set_state_global(ba_engine* e, const double* X, const double* R, const double* t,
+                        const double* f, const double* u, int mem, void* stream);
+int ba_get_state_global(ba_engine* e, int which, double* X, double* K, double* R, double* t,
+                        int mem, void* stream);
 
 /* ---- single kernels / phases (each cites what it replaces) --------------------------- */
 /* _calc_reprojection_error (:666-677): local cost of the current state into the cost buffer

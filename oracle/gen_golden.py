@@ -114,9 +114,9 @@ def _first_linearisation(x, X0, K0, R0, t0, axis, vis=None, f0=1.0, c=1e-4):
     )
 
 
-def case_c1():
-    """Config 1: ``euclidiean_reconstruction.py`` run unchanged (seed 123); the BA inputs
-    it builds (self-calibration output) are captured by wrapping the class constructor."""
+def case_script(script: str, out_name: str):
+    """One of the reference's scripts run unchanged (seed 123); the BA inputs it builds (the
+    self-calibration output) are captured by wrapping the class constructor."""
     _stub_matplotlib()
     import lib.bundle_adjustment as refmod
 
@@ -131,14 +131,26 @@ def case_c1():
     refmod.BundleAdjuster.__init__ = spy
     try:
         with contextlib.redirect_stdout(io.StringIO()):
-            runpy.run_path(os.path.join(REF, "euclidiean_reconstruction.py"), run_name="__main__")
+            runpy.run_path(os.path.join(REF, script), run_name="__main__")
     finally:
         refmod.BundleAdjuster.__init__ = orig_init
     x, X0, K0, R0, t0 = (captured[k] for k in ("x", "X0", "K0", "R0", "t0"))
     out = _run_reference(x, X0, K0, R0, t0, "x-up_z-forward")
     out.update(x=x, X0=X0, K0=K0, R0=R0, t0=t0, axis=np.array("x-up_z-forward"), f0=np.array(1.0))
-    np.savez_compressed(os.path.join(OUT, "c1_euclid.npz"), **out)
-    print("c1_euclid: iterations", len(out["E"]) - 1, "E_final", repr(float(out["E"][-1])))
+    np.savez_compressed(os.path.join(OUT, out_name + ".npz"), **out)
+    print(out_name + ": iterations", len(out["E"]) - 1, "E_final", repr(float(out["E"][-1])))
+
+
+def case_c1():
+    """Config 1: ``euclidiean_reconstruction.py`` (perspective self-calibration init)."""
+    case_script("euclidiean_reconstruction.py", "c1_euclid")
+
+
+def case_affine():
+    """``affine_reconstruction.py`` -- the second caller of the same
+    BundleAdjuster (12 cameras, paraperspective self-calibration init, ``t = -3 R[:, :, 2]``,
+    ``K`` a read-only broadcast of the identity; reference ``affine_reconstruction.py:43-58``)."""
+    case_script("affine_reconstruction.py", "affine_script")
 
 
 def case_small(name, n_cams, n_points, seed, visibility, axis, flip=False, max_iter=100,
@@ -182,7 +194,11 @@ def case_small(name, n_cams, n_points, seed, visibility, axis, flip=False, max_i
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "affine":  # add the one fixture without regenerating the rest
+        case_affine()
+        return
     case_c1()
+    case_affine()
     case_small("small_dense_xup", 6, 40, seed=11, visibility=1.0, axis="x-up_z-forward")
     case_small("small_dense_xright", 5, 32, seed=12, visibility=1.0, axis="x-right_z-forward")
     case_small("small_sparse_xup", 8, 60, seed=13, visibility=0.6, axis="x-up_z-forward")

@@ -26,7 +26,7 @@ def golden():
 
 SMALL_CASES = ["small_dense_xup", "small_dense_xright", "small_sparse_xup",
                "small_sparse_xright", "small_flip_xup"]
-RUN_CASES = ["c1_euclid"] + SMALL_CASES + ["mid_dense_xup", "mid_sparse_xup"]
+RUN_CASES = ["c1_euclid", "affine_script"] + SMALL_CASES + ["mid_dense_xup", "mid_sparse_xup"]
 
 
 def case_inputs(g):

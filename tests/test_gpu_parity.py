@@ -206,6 +206,30 @@ def test_graph_loop_equals_eager_loop(ba, visibility, monkeypatch):
         assert np.array_equal(other[2], runs[0][2])
 
 
+@pytest.mark.parametrize("name", ["small_flip_xup", "small_sparse_xright", "c1_euclid"])
+def test_gauge_on_device_matches_reference_golden(ba, name):
+    """normalise / de-normalise (:208-258) as CUDA kernels, including the
+    reference's negative-divisor quirk (small_flip_xup)."""
+    g = load_golden(name)
+    x, vis, X0, K0, R0, t0, axis, f0 = case_inputs(g)
+    adj = ba.BundleAdjuster(x, X0, K0, R0, t0, f0=f0, visibility_index=vis, axis=axis, gauge_on_device=True)
+    # the normalised state the kernels produced against the host mirror of the reference's transform
+    Xn, Rn, tn = ba.submodule("gauge").normalize(X0, R0, t0, axis)
+    dX, dR, dt, _, _ = adj.engine.get_state(0)
+    np.testing.assert_allclose(dX, Xn, rtol=0, atol=1e-13 * max(1.0, np.abs(Xn).max()))
+    np.testing.assert_allclose(dR, Rn, rtol=0, atol=1e-14)
+    np.testing.assert_allclose(dt, tn, rtol=0, atol=1e-13 * max(1.0, np.abs(tn).max()))
+    with contextlib.redirect_stdout(io.StringIO()):
+        X, K, R, t = adj.optimize(2.0, 1e-8, max_iter=100)
+    E = np.array([adj.records[0]["E_prev"]] + [r["E"] for r in adj.records])
+    assert E.shape == g["E"].shape
+    np.testing.assert_allclose(E, g["E"], rtol=1e-9, atol=0)
+    np.testing.assert_allclose(X, g["X"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(K, g["K"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(R, g["R"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(t, g["t"], rtol=0, atol=1e-6)
+
+
 def test_inputs_are_not_written(ba):
     """The affine script passes a read-only broadcast K (reference affine_reconstruction.py:45)."""
     g = load_golden("small_dense_xup")
