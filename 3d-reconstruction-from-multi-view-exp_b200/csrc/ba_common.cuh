@@ -66,6 +66,11 @@ struct CamState {
 // use their own event pair).
 enum ProfGroup { PG_K1 = 0, PG_K2, PG_K3, PG_K4, PG_COST, PG_OTHER, PG_SYRK, PG_CHOL, PG_COMM, PG_COUNT };
 
+// One CTA of the dense Schur product: tile (ti, tj) of P and the k-chunks [c_lo, c_hi) of Y^T.
+struct SyrkItem {
+  int ti, tj, c_lo, c_hi;
+};
+
 struct Comm;  // peer-memory exchange of a sharded run (comm_peer.cu)
 
 struct ProfSlot {
@@ -94,7 +99,11 @@ struct ba_engine {
   // reduced system layout: n_full = 9M unknown slots (gauge entries pinned, not deleted),
   // row rhs_row = 9M carries the right-hand side, n_pad = padded order = leading dimension
   int n_full = 0, rhs_row = 0, n_pad = 0;
-  int syrk_tile = 128, syrk_splits = 1;
+  int syrk_tile = 128;
+  int syrk_n_items = 0, syrk_n_tiles = 0;
+  ba::SyrkItem* syrk_items = nullptr;  // [syrk_n_items] launch order
+  int* syrk_tile_first = nullptr;      // [syrk_n_tiles + 1]
+  int* syrk_tile_items = nullptr;      // items of each tile in ascending k order
   int64_t k_pad = 0;  // padded 3N (rows of Yt)
 
   // observations (CSR by point) and camera-major index
@@ -130,7 +139,7 @@ struct ba_engine {
   int64_t red_len = 0;
   bool red_in_window = false;  // red lives in the exchange window (freed with it)
   ba::Comm* comm = nullptr;    // non-null: sharded run, sums go through peer memory
-  double* Spart = nullptr;  // split-K partial tiles
+  double* Spart = nullptr;  // partial tiles, one per work item of the Schur product
   double* Lt = nullptr;     // Cholesky block column, k-major copy [kCholOB][n_pad]
   double* ywork = nullptr;  // [n_pad] running right-hand side of the grid-wide back substitution
   unsigned int* chol_bar = nullptr;  // grid barrier counter of that kernel
@@ -247,7 +256,9 @@ int launch_k2a(ba_engine* e, cudaStream_t s, bool conditional);
 int launch_camera_blocks(ba_engine* e, cudaStream_t s, bool conditional);
 int launch_k2b(ba_engine* e, bool conditional, double c_host, cudaStream_t s);
 int launch_k3(ba_engine* e, bool conditional, cudaStream_t s);
-int syrk_choose_splits(int n_pad, int tile, int64_t k_pad, int num_sms);
+int syrk_plan_engine(ba_engine* e);
+int syrk_plan_selftest(int n_cams, int64_t n_points, int tile, int num_sms, int* n_items, int* n_tiles,
+                       double* makespan_rows, double* ideal_rows);
 int launch_assemble(ba_engine* e, bool conditional, double c_host, cudaStream_t s);
 int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s);
 int launch_chol_wide_update(double* S, int ld, int n_rows, int t0, const double* Lt, int depth,

@@ -157,7 +157,7 @@ static void free_engine(ba_engine* e) {
   void* ptrs[] = {e->obs_ptr, e->obs_cam, e->obs_pt, e->obs_xy, e->cam_ptr, e->cm_perm, e->bits, e->PT, e->X[0],
                   e->X[1], e->cam[0].f, e->cam[1].f, e->camtab[0], e->camtab[1], e->JP, e->JC, e->V,
                   e->GPT, e->Upart, e->Uloc, e->LINV, e->Z, e->Yt, e->Ysp, e->red_in_window ? nullptr : e->red, e->Spart, e->Lt, e->Winv,
-                  e->dxi, e->cost_part, e->cost_buf, e->ctl, e->rec, e->ywork, e->chol_bar, e->gauge};
+                  e->dxi, e->cost_part, e->cost_buf, e->ctl, e->rec, e->ywork, e->chol_bar, e->gauge, e->syrk_items, e->syrk_tile_first, e->syrk_tile_items};
   for (void* p : ptrs)
     dev_free(p);
   for (int k = 0; k < 2; ++k) {
@@ -234,14 +234,13 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
   e->n_full = 9 * e->M;
   e->rhs_row = e->n_full;
   const int n_aug = e->n_full + 1;
-  e->syrk_tile = n_aug <= 1024 ? 64 : 128;
+  e->syrk_tile = n_aug <= 384 ? 64 : 128;  // C2 (n = 451): 128-tiles 0.283 ms vs 64-tiles 0.302 ms per iteration
   if (const char* t = std::getenv("BA_SYRK_TILE")) {  // tuning experiments only
     const int v = std::atoi(t);
     if (v == 64 || v == 128) e->syrk_tile = v;
   }
   e->n_pad = round_up(n_aug, 8);  // fragment granularity; edge tiles of the SYRK are partial
   e->k_pad = round_up64(3 * e->N, 32);
-  e->syrk_splits = syrk_choose_splits(e->n_pad, e->syrk_tile, e->k_pad, e->num_sms);
   e->cam_chunks = (4 * e->num_sms + e->M - 1) / e->M;
   if (e->cam_chunks < 1) e->cam_chunks = 1;
   {
@@ -286,8 +285,7 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
   A(dev_alloc(&e->red, (size_t)e->red_len));
   if (e->dense) {
     A(dev_alloc(&e->Yt, (size_t)e->k_pad * e->n_pad));
-    const int nt1 = (e->n_pad + e->syrk_tile - 1) / e->syrk_tile;
-    A(dev_alloc(&e->Spart, (size_t)e->syrk_splits * (nt1 * (nt1 + 1) / 2) * e->syrk_tile * e->syrk_tile));
+    A(syrk_plan_engine(e));
   } else {
     A(dev_alloc(&e->Ysp, (size_t)e->nobs * 27));
   }
@@ -767,5 +765,10 @@ int ba_profile_reset(ba_engine* e) {
 }
 
 int ba_fp64_peak(int device, int use_dmma, double* tflops) { return fp64_peak(device, use_dmma, tflops); }
+
+int ba_syrk_plan_info(int n_cams, int64_t n_points, int tile, int num_sms, int* n_items, int* n_tiles,
+                      double* makespan_rows, double* ideal_rows) {
+  return syrk_plan_selftest(n_cams, n_points, tile, num_sms, n_items, n_tiles, makespan_rows, ideal_rows);
+}
 
 }  // extern "C"

@@ -18,6 +18,14 @@
 // Compute roofline (FP64 tensor): algorithmic flops = 3N * n (n + 1), n = 9M - 7.
 //
 // Sparse visibility: see k3_schur_sparse.cu (output-stationary, no atomics).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <functional>
+#include <mutex>
+#include <queue>
+#include <vector>
+
 #include "ba_common.cuh"
 
 namespace ba {
@@ -55,7 +63,7 @@ __device__ __forceinline__ void tile_from_linear(int t, int& ti, int& tj) {
 template <int TILE, int WR, int WC, int KC, bool SUB>
 __global__ void __launch_bounds__(WR* WC * 32)
 syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_chunks,
-                 int chunks_per_split, int n_tiles, double* __restrict__ part,
+                 const SyrkItem* __restrict__ items, double* __restrict__ part,
                  const ba_lm_state* ctl, int n_store) {
   if (ctl && ctl->done) return;
   constexpr int NT = WR * WC * 32;
@@ -67,15 +75,19 @@ syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_c
   static_assert(KC * CPR % NT == 0, "stage copy must divide evenly");
   extern __shared__ __align__(16) double smem[];
 
-  const int t = blockIdx.x;
+  // work item: a tile and a range of k-chunks (Schur product), or the whole depth of tile
+  // blockIdx.x (trailing update)
   int ti, tj;
-  tile_from_linear(t, ti, tj);
+  int64_t c_lo, c_hi;
+  if (SUB) {
+    tile_from_linear(blockIdx.x, ti, tj);
+    c_lo = 0;
+    c_hi = n_chunks;
+  } else {
+    const SyrkItem it = items[blockIdx.x];
+    ti = it.ti; tj = it.tj; c_lo = it.c_lo; c_hi = it.c_hi;
+  }
   const bool diag = ti == tj;
-
-  const int split = blockIdx.y;
-  const int64_t c_lo = (int64_t)split * chunks_per_split;
-  int64_t c_hi = c_lo + chunks_per_split;
-  if (c_hi > n_chunks) c_hi = n_chunks;
   const int nk = (int)(c_hi > c_lo ? c_hi - c_lo : 0);
 
   double* sA = smem;                                // [stage][KC][LDS]
@@ -110,7 +122,21 @@ syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_c
   };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wr = warp / WC, wc = warp % WC;
+  // Sub-tile of this warp.  Off the diagonal: row-major over the WR x WC grid.  On a diagonal
+  // tile only the WR (WR + 1) / 2 sub-tiles on or below the diagonal are needed (nothing above
+  // the diagonal is read anywhere); they are dealt to warps 0, 1, 2, ... -- consecutive warps sit
+  // on different scheduler partitions, so the 10 (of 16) live warps of a 128-tile load the four
+  // FP64 pipes 3/3/2/2 instead of 4/3/2/1 -- and the remaining warps only help with the copies.
+  int wr = warp / WC, wc = warp % WC;
+  bool live = true;
+  if (diag && WR == WC) {
+    live = warp < WR * (WR + 1) / 2;
+    if (live) {
+      wr = 0;
+      while ((wr + 1) * (wr + 2) / 2 <= warp) ++wr;
+      wc = warp - wr * (wr + 1) / 2;
+    }
+  }
   const int row0 = wr * WM + (lane >> 2);
   const int col0 = wc * WN + (lane >> 2);
   const int kq = lane & 3;
@@ -121,9 +147,7 @@ syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_c
   for (int i = 0; i < FM; ++i) vm += (ti * TILE + wr * WM + 8 * i) < n_valid;
 #pragma unroll
   for (int j = 0; j < FN; ++j) vn += (tj * TILE + wc * WN + 8 * j) < n_valid;
-  // on a diagonal tile the warps whose sub-tile lies strictly above the diagonal have nothing to
-  // compute (nothing above the diagonal is read anywhere): they only help with the copies
-  if (diag && WM == WN && wc > wr) vm = 0;
+  if (!live) vm = 0;
   const bool full = vm == FM && vn == FN;
 
   double acc[FM][FN][2];
@@ -178,6 +202,7 @@ syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_c
 
   const int orow = wr * WM + (lane >> 2);
   const int ocol = wc * WN + 2 * (lane & 3);
+  if (!live) return;  // the sub-tiles above the diagonal of a diagonal tile are never read
   if (SUB) {
     // S -= acc on the lower triangle; an accumulator pair sits at (r, c), (r, c + 1), c even
 #pragma unroll
@@ -198,8 +223,8 @@ syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_c
       }
     return;
   }
-  // partial tile [split][tile][TILE][TILE]
-  double* out = part + ((size_t)split * n_tiles + t) * TILE * TILE;
+  // partial tile of this item: part[item][TILE][TILE]
+  double* out = part + (size_t)blockIdx.x * TILE * TILE;
 #pragma unroll
   for (int i = 0; i < FM; ++i)
 #pragma unroll
@@ -208,34 +233,39 @@ syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_c
           make_double2(acc[i][j][0], acc[i][j][1]);
 }
 
-// P[tile] = sum over splits in a fixed order, restricted to the valid part of P.
+// P[tile] = sum of the tile's items in a fixed order (ascending k range), restricted to the valid
+// part of P and, on diagonal tiles, to the pairs that touch the lower triangle.
 template <int TILE>
 __global__ void __launch_bounds__(256)
-syrk_reduce_kernel(const double* __restrict__ part, int n_tiles, int splits, double* __restrict__ P,
-                   int ld, int n_valid, const ba_lm_state* ctl) {
+syrk_reduce_kernel(const double* __restrict__ part, const int* __restrict__ tile_first,
+                   const int* __restrict__ tile_items, double* __restrict__ P, int ld, int n_valid,
+                   const ba_lm_state* ctl) {
   if (ctl && ctl->done) return;
   const int t = blockIdx.x;
   int ti, tj;
   tile_from_linear(t, ti, tj);
+  const int first = tile_first[t], cnt = tile_first[t + 1] - first;
+  const int* slots = tile_items + first;
+  constexpr size_t TT = (size_t)TILE * TILE;
   // blockIdx.y picks a slab of rows of the tile; 4 independent loads in flight per thread
   const int per = TILE * TILE / 2 / gridDim.y;
   for (int q = blockIdx.y * per + threadIdx.x; q < (blockIdx.y + 1) * per; q += blockDim.x) {
     const int r = q / (TILE / 2), c = 2 * (q % (TILE / 2));
     if (ti * TILE + r >= n_valid || tj * TILE + c >= n_valid) continue;
-    const double* src = part + (size_t)t * TILE * TILE + (size_t)r * TILE + c;
-    const size_t stride = (size_t)n_tiles * TILE * TILE;
+    if (ti == tj && c > r) continue;
+    const double* src = part + (size_t)r * TILE + c;
     double2 s = make_double2(0.0, 0.0);
     int sp = 0;
-    for (; sp + 4 <= splits; sp += 4) {
-      const double2 v0 = *reinterpret_cast<const double2*>(src + (size_t)sp * stride);
-      const double2 v1 = *reinterpret_cast<const double2*>(src + (size_t)(sp + 1) * stride);
-      const double2 v2 = *reinterpret_cast<const double2*>(src + (size_t)(sp + 2) * stride);
-      const double2 v3 = *reinterpret_cast<const double2*>(src + (size_t)(sp + 3) * stride);
+    for (; sp + 4 <= cnt; sp += 4) {
+      const double2 v0 = *reinterpret_cast<const double2*>(src + slots[sp] * TT);
+      const double2 v1 = *reinterpret_cast<const double2*>(src + slots[sp + 1] * TT);
+      const double2 v2 = *reinterpret_cast<const double2*>(src + slots[sp + 2] * TT);
+      const double2 v3 = *reinterpret_cast<const double2*>(src + slots[sp + 3] * TT);
       s.x = (((s.x + v0.x) + v1.x) + v2.x) + v3.x;
       s.y = (((s.y + v0.y) + v1.y) + v2.y) + v3.y;
     }
-    for (; sp < splits; ++sp) {
-      const double2 v = *reinterpret_cast<const double2*>(src + (size_t)sp * stride);
+    for (; sp < cnt; ++sp) {
+      const double2 v = *reinterpret_cast<const double2*>(src + slots[sp] * TT);
       s.x += v.x;
       s.y += v.y;
     }
@@ -255,61 +285,185 @@ __global__ void stage_camera_blocks_kernel(int n, const double* __restrict__ src
 static inline int syrk_kc(int tile) { return tile == 128 ? 32 : 16; }
 static inline int syrk_occupancy(int tile) { return tile == 128 ? 1 : 4; }
 
-// Number of K splits: enough CTAs (tiles x splits) to keep every SM slot busy through the tail,
-// each still streaming >= 768 k-rows, preferring counts that fill whole waves.
-int syrk_choose_splits(int n_pad, int tile, int64_t k_pad, int num_sms) {
-  const int nt1 = (n_pad + tile - 1) / tile;
-  const int n_tiles = nt1 * (nt1 + 1) / 2;
-  const int64_t n_chunks = k_pad / syrk_kc(tile);
-  const int slots = num_sms * syrk_occupancy(tile);
-  const int64_t min_chunks = 768 / syrk_kc(tile);
-  int64_t s_max = n_chunks / min_chunks;
-  if (s_max < 1) s_max = 1;
-  int64_t s_cap = (int64_t)24 * slots / n_tiles;
-  if (s_cap < 1) s_cap = 1;
-  // All tiles of one split stream the same k-slab of Yt (k_pad / splits rows x n_pad columns).
-  // Tiles drift apart (diagonal and edge tiles do less work), so the slab is only served from L2
-  // if it fits there as a whole: ncu showed 18.6 GB of DRAM reads for the 4.3 GB operand of C3
-  // with 271 MB slabs.  Ask for slabs of at most 48 MB (of the 126 MB L2) when K allows it.
-  const int64_t slab_cap = (int64_t)48 << 20;
-  int64_t s_l2 = ((int64_t)k_pad * n_pad * 8 + slab_cap - 1) / slab_cap;
-  if (s_l2 > s_max) s_l2 = s_max;
-  if (s_cap < s_l2) s_cap = s_l2;
-  const int s_hi = (int)(s_max < s_cap ? s_max : s_cap);
-  int best = s_hi;
-  double best_eff = 0.0;
-  for (int s = s_hi; s >= (s_hi + 1) / 2 && s >= 1; --s) {
-    const int64_t items = (int64_t)n_tiles * s;
-    const int64_t waves = (items + slots - 1) / slots;
-    const double eff = (double)items / (double)(waves * slots);
-    if (eff > best_eff + 1e-9) {
-      best_eff = eff;
-      best = s;
+// Relative duration of a tile per k-row (1 = full tile), mirroring the kernel's warp mapping:
+// edge tiles skip the 8x8 fragments beyond n_valid, diagonal tiles the sub-tiles above the
+// diagonal.  A warp sits on scheduler partition (warp % 4) with its own FP64 pipe: a CTA that has
+// an SM to itself takes as long as its busiest partition; with several CTAs per SM the partitions
+// even out and the mean counts.
+static double tile_weight(int TILE, int WR, int WC, int occ, int ti, int tj, int n_valid) {
+  const int WM = TILE / WR, WN = TILE / WC, FM = WM / 8, FN = WN / 8;
+  double load[4] = {0, 0, 0, 0};
+  for (int warp = 0; warp < WR * WC; ++warp) {
+    int wr = warp / WC, wc = warp % WC;
+    bool live = true;
+    if (ti == tj && WR == WC) {
+      live = warp < WR * (WR + 1) / 2;
+      if (live) {
+        wr = 0;
+        while ((wr + 1) * (wr + 2) / 2 <= warp) ++wr;
+        wc = warp - wr * (wr + 1) / 2;
+      }
     }
+    int vm = 0, vn = 0;
+    for (int i = 0; i < FM; ++i) vm += (ti * TILE + wr * WM + 8 * i) < n_valid;
+    for (int j = 0; j < FN; ++j) vn += (tj * TILE + wc * WN + 8 * j) < n_valid;
+    if (live) load[warp % 4] += (double)vm * vn;
   }
-  return best;
+  const double per_part = (double)FM * FN * ((WR * WC + 3) / 4);
+  const double mx = std::max(std::max(load[0], load[1]), std::max(load[2], load[3]));
+  const double mean = (load[0] + load[1] + load[2] + load[3]) / 4.0;
+  const double w = (occ == 1 ? mx : mean) / per_part;
+  // A CTA pays for every k-row it streams whatever it computes on it (copies, barrier, pipeline
+  // bookkeeping): tiles with little tensor work are bounded by that floor, not by their DMMA count.
+  // Measured at C2 (50 x 10k): the 64-tile kernel (four CTAs per SM) is fastest with uniform cuts
+  // (floor 1.0: 0.302 ms per iteration, 0.75: 0.309, 0.5: 0.344, 0.35: 0.430); the 128-tile
+  // kernel with floor 0.75 (1.0: 0.326, 0.75: 0.283, 0.5: 0.343, 0.35: 0.355).
+  double floor_w = occ == 1 ? 0.75 : 1.0;
+  if (const char* f = std::getenv("BA_SYRK_FLOOR")) floor_w = std::atof(f);  // tuning experiments only
+  return w > floor_w ? w : floor_w;
+}
+
+struct SyrkPlan {
+  std::vector<SyrkItem> items;       // launch order: ascending k range, then tile
+  std::vector<int> tile_first;       // [n_tiles + 1]
+  std::vector<int> tile_items;       // item index per (tile, piece), pieces in ascending k order
+  double makespan = 0.0;             // modelled duration in k-rows of a full tile on one SM slot
+};
+
+// Cut every tile's K range into pieces so that all CTAs take about the same time and their number
+// fills whole waves of SM slots: pieces(t) ~ weight(t) x S.  S is chosen by simulating the block
+// scheduler (CTAs start in launch order on the first free slot) for every admissible S and
+// keeping the shortest schedule.  Constraints: a piece streams >= 512 k-rows (prologue, epilogue
+// and the partial-tile write stay small against it), and -- L2 residency -- the k-slab that the
+// CTAs of one "column" of the schedule share should stay below 48 MB: ncu showed 18.6 GB of DRAM
+// reads for the 4.3 GB operand of C3 when 271 MB slabs were streamed by tiles drifting apart.
+static SyrkPlan plan_syrk(int n_pad, int TILE, int WR, int WC, int64_t k_pad, int num_sms) {
+  const int KC = syrk_kc(TILE), occ = syrk_occupancy(TILE);
+  const int nt1 = (n_pad + TILE - 1) / TILE;
+  const int n_tiles = nt1 * (nt1 + 1) / 2;
+  const int64_t n_chunks = k_pad / KC;
+  const int slots = num_sms * occ;
+  std::vector<double> w(n_tiles);
+  for (int t = 0, ti = 0; ti < nt1; ++ti)
+    for (int tj = 0; tj <= ti; ++tj, ++t) w[t] = tile_weight(TILE, WR, WC, occ, ti, tj, n_pad);
+  const int64_t min_chunks = std::max<int64_t>(1, 512 / KC);
+  const int64_t s_max = std::max<int64_t>(1, n_chunks / min_chunks);
+  const int64_t slab_cap = (int64_t)48 << 20;
+  const int64_t s_l2 = std::min<int64_t>(s_max, (k_pad * (int64_t)n_pad * 8 + slab_cap - 1) / slab_cap);
+  const int64_t s_cap = std::min<int64_t>(s_max, std::max<int64_t>(s_l2, std::max<int64_t>(1, (int64_t)24 * slots / n_tiles)));
+  const int64_t s_lo = std::max<int64_t>(1, std::min<int64_t>(s_l2, s_cap));
+  const double overhead = 48.0;  // k-rows of a full tile: pipeline fill + partial-tile write
+
+  auto build = [&](int64_t S, SyrkPlan* out) -> double {
+    struct Piece { int t; int64_t lo, hi; };
+    std::vector<Piece> pieces;
+    std::vector<int> count(n_tiles);
+    for (int t = 0; t < n_tiles; ++t) {
+      int64_t p = (int64_t)std::llround(w[t] * (double)S);
+      p = std::max<int64_t>(1, std::min<int64_t>(p, s_max));
+      const int64_t cps = (n_chunks + p - 1) / p;
+      p = (n_chunks + cps - 1) / cps;
+      count[t] = (int)p;
+      for (int64_t k = 0; k < p; ++k) pieces.push_back({t, k * cps, std::min<int64_t>(n_chunks, (k + 1) * cps)});
+    }
+    std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& a, const Piece& b) {
+      return a.lo != b.lo ? a.lo < b.lo : a.t < b.t;
+    });
+    // list scheduling on `slots` slots, each running at 1/occ of an SM
+    std::priority_queue<double, std::vector<double>, std::greater<double>> free_at;
+    for (int k = 0; k < slots; ++k) free_at.push(0.0);
+    double makespan = 0.0;
+    for (const Piece& pc : pieces) {
+      const double start = free_at.top();
+      free_at.pop();
+      const double end = start + (w[pc.t] * (double)(pc.hi - pc.lo) * KC + overhead) * occ;
+      free_at.push(end);
+      makespan = std::max(makespan, end);
+    }
+    if (out) {
+      out->items.clear();
+      out->tile_first.assign(n_tiles + 1, 0);
+      for (int t = 0; t < n_tiles; ++t) out->tile_first[t + 1] = out->tile_first[t] + count[t];
+      out->tile_items.assign(out->tile_first[n_tiles], 0);
+      std::vector<int> fill(n_tiles, 0);
+      std::vector<int> ti_of(n_tiles), tj_of(n_tiles);
+      for (int t = 0, ti = 0; ti < nt1; ++ti)
+        for (int tj = 0; tj <= ti; ++tj, ++t) { ti_of[t] = ti; tj_of[t] = tj; }
+      for (const Piece& pc : pieces) {  // sorted by lo: per tile the pieces arrive in ascending k order
+        out->tile_items[out->tile_first[pc.t] + fill[pc.t]++] = (int)out->items.size();
+        out->items.push_back({ti_of[pc.t], tj_of[pc.t], (int)pc.lo, (int)pc.hi});
+      }
+      out->makespan = makespan;
+    }
+    return makespan;
+  };
+
+  int64_t best_S = s_lo;
+  double best = 1e300;
+  for (int64_t S = s_lo; S <= s_cap; ++S) {
+    const double m = build(S, nullptr);
+    if (m < best * (1.0 - 1e-9)) { best = m; best_S = S; }
+  }
+  SyrkPlan plan;
+  build(best_S, &plan);
+  return plan;
+}
+
+// Plans are kept for the life of the process: the schedule search costs milliseconds of host
+// time, more than a small adjustment, and callers adjust scene after scene of the same shape.
+static const SyrkPlan& cached_plan(int n_pad, int tile, int64_t k_pad, int num_sms) {
+  struct Key { int n_pad, tile; int64_t k_pad; int sms; };
+  static std::mutex mu;
+  static std::vector<std::pair<Key, SyrkPlan*>> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto& kv : cache)
+    if (kv.first.n_pad == n_pad && kv.first.tile == tile && kv.first.k_pad == k_pad && kv.first.sms == num_sms)
+      return *kv.second;
+  SyrkPlan* p = new SyrkPlan(tile == 128 ? plan_syrk(n_pad, 128, 4, 4, k_pad, num_sms)
+                                         : plan_syrk(n_pad, 64, 2, 2, k_pad, num_sms));
+  cache.push_back({Key{n_pad, tile, k_pad, num_sms}, p});
+  return *p;
+}
+
+// Plans the dense Schur product of this engine and uploads the work items.
+int syrk_plan_engine(ba_engine* e) {
+  if (!e->dense) return BA_OK;
+  const SyrkPlan& plan = cached_plan(e->n_pad, e->syrk_tile, e->k_pad, e->num_sms);
+  e->syrk_n_items = (int)plan.items.size();
+  const int nt1 = (e->n_pad + e->syrk_tile - 1) / e->syrk_tile;
+  e->syrk_n_tiles = nt1 * (nt1 + 1) / 2;
+  const size_t tt = (size_t)e->syrk_tile * e->syrk_tile;
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&e->syrk_items), plan.items.size() * sizeof(SyrkItem), (cudaStream_t)0));
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&e->syrk_tile_first), plan.tile_first.size() * sizeof(int), (cudaStream_t)0));
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&e->syrk_tile_items), plan.tile_items.size() * sizeof(int), (cudaStream_t)0));
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&e->Spart), plan.items.size() * tt * sizeof(double), (cudaStream_t)0));
+  BA_CUDA(cudaMemcpy(e->syrk_items, plan.items.data(), plan.items.size() * sizeof(SyrkItem), cudaMemcpyHostToDevice));
+  BA_CUDA(cudaMemcpy(e->syrk_tile_first, plan.tile_first.data(), plan.tile_first.size() * sizeof(int), cudaMemcpyHostToDevice));
+  BA_CUDA(cudaMemcpy(e->syrk_tile_items, plan.tile_items.data(), plan.tile_items.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (std::getenv("BA_TIMING"))
+    std::fprintf(stderr, "[ba syrk plan] tile %d: %d tiles, %d items on %d slots, modelled %.0f k-rows (ideal %.0f)\n",
+                 e->syrk_tile, e->syrk_n_tiles, e->syrk_n_items, e->num_sms * syrk_occupancy(e->syrk_tile),
+                 plan.makespan, 0.0);
+  return BA_OK;
 }
 
 template <int TILE, int WR, int WC, int KC>
 static int launch_syrk(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
-  const int nt1 = (e->n_pad + TILE - 1) / TILE;
-  const int n_tiles = nt1 * (nt1 + 1) / 2;
   const int64_t n_chunks = e->k_pad / KC;
-  const int splits = e->syrk_splits;
-  const int cps = (int)((n_chunks + splits - 1) / splits);
   const size_t smem = (size_t)2 * kStages * KC * (TILE + 4) * sizeof(double);
   BA_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<TILE, WR, WC, KC, false>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(n_tiles, splits);
   {
     ProfScope ps(e, PG_SYRK, s);
-    syrk_dmma_kernel<TILE, WR, WC, KC, false><<<grid, WR * WC * 32, smem, s>>>(
-        e->Yt, e->n_pad, e->n_pad, n_chunks, cps, n_tiles, e->Spart, ctl, 0);
+    syrk_dmma_kernel<TILE, WR, WC, KC, false><<<e->syrk_n_items, WR * WC * 32, smem, s>>>(
+        e->Yt, e->n_pad, e->n_pad, n_chunks, e->syrk_items, e->Spart, ctl, 0);
     BA_LAUNCH_CHECK();
   }
+  const int n_tiles = e->syrk_n_tiles;
   const int slabs = n_tiles >= 4 * e->num_sms ? 1 : (n_tiles >= e->num_sms ? 4 : 8);
-  syrk_reduce_kernel<TILE><<<dim3(n_tiles, slabs), 256, 0, s>>>(e->Spart, n_tiles, splits, e->P(),
-                                                               e->n_pad, e->n_pad, ctl);
+  syrk_reduce_kernel<TILE><<<dim3(n_tiles, slabs), 256, 0, s>>>(e->Spart, e->syrk_tile_first,
+                                                               e->syrk_tile_items, e->P(), e->n_pad,
+                                                               e->n_pad, ctl);
   BA_LAUNCH_CHECK();
   return BA_OK;
 }
@@ -327,8 +481,8 @@ static int launch_syrk_sub(double* S, int ld, int n_rows, int t0, const double* 
   const size_t smem = (size_t)2 * kStages * KC * (TILE + 4) * sizeof(double);
   BA_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<TILE, WR, WC, KC, true>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  syrk_dmma_kernel<TILE, WR, WC, KC, true><<<dim3(n_tiles, 1), WR * WC * 32, smem, s>>>(
-      Lt + t0, ld, n_valid, n_chunks, n_chunks, n_tiles, S + (size_t)t0 * ld + t0, ctl, n_store);
+  syrk_dmma_kernel<TILE, WR, WC, KC, true><<<n_tiles, WR * WC * 32, smem, s>>>(
+      Lt + t0, ld, n_valid, n_chunks, nullptr, S + (size_t)t0 * ld + t0, ctl, n_store);
   BA_LAUNCH_CHECK();
   return BA_OK;
 }
@@ -352,6 +506,41 @@ int launch_k3(ba_engine* e, bool conditional, cudaStream_t s) {
     return launch_syrk<64, 2, 2, 16>(e, ctl, s);
   }
   return launch_schur_sparse(e, ctl, s);
+}
+
+// Host-only check of the planner (no device needed): every tile's pieces must tile [0, n_chunks)
+// exactly once, in ascending order.
+int syrk_plan_selftest(int n_cams, int64_t n_points, int tile, int num_sms, int* n_items, int* n_tiles,
+                       double* makespan_rows, double* ideal_rows) {
+  const int n_pad = (9 * n_cams + 1 + 7) / 8 * 8;
+  const int64_t k_pad = (3 * n_points + 31) / 32 * 32;
+  if (tile != 64 && tile != 128) { set_error("tile must be 64 or 128"); return BA_ERR_INVALID; }
+  const SyrkPlan& plan = cached_plan(n_pad, tile, k_pad, num_sms);
+  const int64_t n_chunks = k_pad / syrk_kc(tile);
+  const int nt = (int)plan.tile_first.size() - 1;
+  double work = 0.0;
+  for (int t = 0; t < nt; ++t) {
+    int64_t pos = 0;
+    for (int k = plan.tile_first[t]; k < plan.tile_first[t + 1]; ++k) {
+      const SyrkItem& it = plan.items[plan.tile_items[k]];
+      int ti = 0;
+      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+      if (it.ti != ti || it.tj != t - ti * (ti + 1) / 2 || it.c_lo != pos || it.c_hi <= it.c_lo) {
+        set_error("plan: tile %d piece %d covers [%d, %d), expected to start at %lld", t, k, it.c_lo, it.c_hi, (long long)pos);
+        return BA_ERR_STATE;
+      }
+      pos = it.c_hi;
+    }
+    if (pos != n_chunks) { set_error("plan: tile %d ends at chunk %lld of %lld", t, (long long)pos, (long long)n_chunks); return BA_ERR_STATE; }
+    int ti = 0;
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    work += tile_weight(tile, tile == 128 ? 4 : 2, tile == 128 ? 4 : 2, syrk_occupancy(tile), ti, t - ti * (ti + 1) / 2, n_pad) * (double)k_pad;
+  }
+  if (n_items) *n_items = (int)plan.items.size();
+  if (n_tiles) *n_tiles = nt;
+  if (makespan_rows) *makespan_rows = plan.makespan;
+  if (ideal_rows) *ideal_rows = work / num_sms;
+  return BA_OK;
 }
 
 }  // namespace ba

@@ -43,6 +43,7 @@ SCALE, TOL_NEVER = 2.0, -1.0  # optimize(2.0, ...) as in the reference script; t
 # bounded CPU samples (points of the named scene, cameras unchanged, LM iterations)
 CPU_SAMPLE = {"c2": (10_000, 2), "c3": (1_500, 1), "c4": (250, 1), "c5": (250, 1)}
 E2E_REPS = 3
+CHUNK = 10  # LM iterations per run from the perturbed start (see run_iters)
 REF_STEP_SAMPLE = {"c2": 2_000, "c3": 800, "c4": 150, "c5": 150}
 
 
@@ -81,7 +82,8 @@ def describe(name: str, cfg: dict, world: int, nobs_total: int, exchange: str = 
                     + (f", {cfg['outlier_frac']:.0%} outliers" if cfg.get("outlier_frac") else ""),
         "n_cams": cfg["n_cams"], "n_points_per_gpu": cfg["n_points"], "observations_total": nobs_total,
         "unknowns_reduced": 9 * cfg["n_cams"] - 7,
-        "lm": "optimize(scale_factor=2.0), one step = one accepted LM iteration from the perturbed start",
+        "lm": "optimize(scale_factor=2.0), one step = one accepted LM iteration; K steps = LM runs of <= 10 "
+              "iterations from the perturbed start (the state is reset on the device between runs)",
         "parallelism": f"points sharded over {world} GPU(s), cameras replicated; {exchange}" if world > 1 else "single GPU",
         "l2": "no flush: iterations are data-dependent; per-iteration working set "
               "(Jacobian rows + Y) exceeds the 126 MB L2 for c2 and larger",
@@ -150,6 +152,16 @@ def oracle_run(sc, n_points: int, iters: int):
     dt = time.perf_counter() - t0
     done = len(ora.trace) - 1
     return hi * done / dt, dt, hi, done, float(np.sqrt(ora.trace[-1]["E"] / hi))
+
+
+def measured_traffic(workload: str):
+    """DRAM bytes per launch of the workload's dominant kernel from the committed `ncu --set full`
+    capture (profiles/roofline_traffic.json names the summary file each figure comes from)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
 
 
 def blas_threads() -> int:
@@ -233,12 +245,28 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
 
     def run_iters(adj, n):
-        """Exactly n accepted LM iterations from the adjuster's stored initial state."""
+        """Exactly n accepted LM iterations, as LM runs of at most CHUNK iterations, each started
+        from the adjuster's initial state (kept on the device).  A run from the perturbed start
+        needs ~14 iterations to reach the noise floor; there the accept test E_ > E is decided
+        by the last bits of the cost sum, so the number of retries would depend on the summation
+        order (hence on the GPU count) instead of on the work.  Chunks stay clear of the floor."""
         eng = adj.engine
-        eng.set_state(adj._X, adj._R, adj._t, adj._f, adj._u)
-        if world > 1 and not adj._peer_exchange:
-            return sharded.lm_loop(eng, dist, group, SCALE, TOL_NEVER, n)
-        _, st = eng.lm_run(SCALE, TOL_NEVER, n)
+        if getattr(adj, "_dev_init", None) is None:
+            adj._dev_init = [torch.from_numpy(np.ascontiguousarray(a)).cuda(local_rank)
+                             for a in (adj._X, adj._R, adj._t, adj._f, adj._u)]
+        done, solves, st = 0, 0, None
+        while done < n:
+            m = min(CHUNK, n - done)
+            eng.set_state(*adj._dev_init)
+            if world > 1 and not adj._peer_exchange:
+                st = sharded.lm_loop(eng, dist, group, SCALE, TOL_NEVER, m)
+            else:
+                _, st = eng.lm_run(SCALE, TOL_NEVER, m)
+            assert st.count == m, f"ran {st.count} iterations instead of {m}"
+            done += m
+            solves += st.solves
+        st.solves = solves
+        st.count = done
         return st
 
     sampler = ClockSampler(local_rank)
@@ -249,7 +277,6 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     adj = make_adjuster()
     if W > 0:
         run_iters(adj, W)
-    adj.engine.set_state(adj._X, adj._R, adj._t, adj._f, adj._u)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches0 = engine_mod.launch_count()
@@ -291,7 +318,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
         eng = adj.engine
         eng.profile_enable(True)
         eng.profile_reset()
-        run_iters(adj, K)
+        st_prof = run_iters(adj, K)
         prof = eng.profile()
         eng.profile_enable(False)
         n_red = 9 * sc.n_cams - 7
@@ -314,7 +341,7 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
             }
         else:
             k3 = prof["k3"]
-            avg_ms = k3["ms"] / max(adj.engine.lm_state().solves, 1)
+            avg_ms = k3["ms"] / max(st_prof.solves, 1)
             achieved = flops / (avg_ms * 1e-3) / 1e12
             out["roofline"] = {
                 "kernel": "schur_pairs_kernel + schur_diag_kernel (K3, sparse Schur products, matrix-free pair kernel)",
@@ -323,6 +350,10 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
                 "avg_launch_ms": avg_ms, "share_of_step": k3["ms"] / tot if tot > 0 else None,
                 "peak_source": "measured live: register-resident DMMA.8x8x4 loop (ba_fp64_peak)",
             }
+        tr = measured_traffic(args.workload)
+        if tr:
+            out["roofline"]["traffic"] = tr["dram_bytes_per_launch"]
+            out["roofline"]["traffic_source"] = tr["source"]
         out["phase_ms_per_step"] = {k: v["ms"] / K for k, v in prof.items()}
         hbm = None
         try:
@@ -356,31 +387,36 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
     # Each repetition is the complete user call for K steps; the median of E2E_REPS wall times is
     # reported (all samples are listed), since a single cold call is dominated by allocator noise.
     state_bytes = (3 * sc.n_points + 15 * sc.n_cams) * 8
-    h2d = h_xy.nbytes + h_ptr.nbytes + (0 if h_cam is None else h_cam.nbytes) + state_bytes
-    d2h = state_bytes + K * 40 + (st.solves + 1) * 88
+    n_calls = (K + CHUNK - 1) // CHUNK
+    h2d = n_calls * (h_xy.nbytes + h_ptr.nbytes + (0 if h_cam is None else h_cam.nbytes) + state_bytes)
+    d2h = n_calls * state_bytes + K * 40 + (st.solves + n_calls) * 88
     e2e_samples = []
+    calls = [min(CHUNK, K - k0) for k0 in range(0, K, CHUNK)]
     for _ in range(E2E_REPS):
         barrier()
         t0 = time.perf_counter()
-        adj2 = make_adjuster(gauge_on_device=True)
-        with contextlib.redirect_stdout(io.StringIO()):
-            Xr, Kr, Rr, tr = adj2.optimize(SCALE, TOL_NEVER, max_iter=K)
+        for m in calls:
+            adj2 = make_adjuster(gauge_on_device=True)
+            with contextlib.redirect_stdout(io.StringIO()):
+                Xr, Kr, Rr, tr = adj2.optimize(SCALE, TOL_NEVER, max_iter=m)
+            assert len(adj2.records) == m
+            adj2.engine.close()
         torch.cuda.synchronize()
         e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         e2e_samples.append(float(e2e_t.item()))
-        assert len(adj2.records) == K
-        adj2.engine.close()
     e2e_s = float(np.median(e2e_samples))
 
     if rank == 0:
         out["e2e"] = {"value": nobs_total * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / K,
                       "d2h_bytes_per_step": d2h / K, "ms_per_step": e2e_s / K * 1e3,
                       "samples_ms_per_step": [t / K * 1e3 for t in e2e_samples],
-                      "what": "BundleAdjuster.from_observations(pinned host arrays).optimize(max_iter=K): "
-                              "engine creation (device memory from the library's retained pool), H2D, "
-                              f"K iterations, D2H of X/K/R/t; median of {E2E_REPS} such calls"}
+                      "what": f"{n_calls} complete user call(s) of <= {CHUNK} iterations each: "
+                              "BundleAdjuster.from_observations(pinned host arrays, gauge_on_device=True)"
+                              ".optimize(max_iter=...): engine creation (device memory from the library's "
+                              "retained pool), H2D of observations and state, gauge normalisation, LM "
+                              f"iterations, de-normalisation, D2H of X/K/R/t; median of {E2E_REPS} repetitions"}
 
     if rank == 0:
         out["clocks"] = sampler.stop(t_wall0, t_wall1)

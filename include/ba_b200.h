@@ -227,6 +227,12 @@ int ba_profile_get(ba_engine* e, const char* group, double* total_ms, int64_t* l
 int ba_profile_reset(ba_engine* e);
 /* FP64 peak micro-benchmarks (register-resident DMMA.8x8x4 / DFMA loops): TFLOP/s. */
 int ba_fp64_peak(int device, int use_dmma, double* tflops);
+/* Host-only (no device): plan the dense Schur product (K3) of an n_cams x n_points scene for a GPU
+ * with num_sms SMs and `tile` = 64 or 128, verify that the work items cover every tile's K range
+ * exactly once, and report the number of items / tiles and the modelled schedule length against
+ * the perfectly balanced one (both in k-rows of a full tile per SM). */
+int ba_syrk_plan_info(int n_cams, int64_t n_points, int tile, int num_sms, int* n_items, int* n_tiles,
+                      double* makespan_rows, double* ideal_rows);
 
 /* ---- next to the path: batched re-projection ------------------------------------------- */
 /* calc_projected_points (reference lib/camera.py:74-81, Camera.project_points :18-32): project

@@ -180,3 +180,27 @@ def test_oracle_sharded_partials_sum_to_the_whole():
         Utot[9 * i: 9 * i + 9, 9 * i: 9 * i + 9] = blk
     np.testing.assert_allclose(Utot - Psum, A, rtol=0, atol=1e-10 * np.abs(A).max())
     np.testing.assert_allclose(bsum, b, rtol=0, atol=1e-10 * np.abs(b).max())
+
+
+@pytest.mark.parametrize("n_cams,n_points,tile", [(50, 10_000, 64), (50, 10_000, 128), (200, 100_000, 128),
+                                                  (17, 333, 64), (120, 900, 128), (2, 5, 64)])
+def test_schur_product_plan_covers_every_tile_once(n_cams, n_points, tile):
+    """The host-side scheduler of the dense Schur product (K3): the work items must cut every
+    lower-triangle tile's K range into consecutive pieces without gaps or overlaps, and the
+    modelled schedule of the benchmark shapes must stay within 15 % of the perfectly balanced one
+    (library self-check through the C ABI; no device involved)."""
+    import ctypes as C
+
+    import ba_b200
+
+    cabi = ba_b200.submodule("_cabi")
+    lib = cabi.load()
+    ni, nt, mk, ideal = C.c_int(), C.c_int(), C.c_double(), C.c_double()
+    cabi.check(lib.ba_syrk_plan_info(n_cams, n_points, tile, 148, C.byref(ni), C.byref(nt), C.byref(mk),
+                                     C.byref(ideal)))
+    n_pad = (9 * n_cams + 1 + 7) // 8 * 8
+    nt1 = (n_pad + tile - 1) // tile
+    assert nt.value == nt1 * (nt1 + 1) // 2
+    assert ni.value >= nt.value
+    if n_points >= 10_000:
+        assert ideal.value / mk.value > 0.85
