@@ -241,11 +241,13 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
   }
   e->n_pad = round_up(n_aug, 8);  // fragment granularity; edge tiles of the SYRK are partial
   e->k_pad = round_up64(3 * e->N, 32);
-  e->cam_chunks = (4 * e->num_sms + e->M - 1) / e->M;
+  // camera_blocks_kernel: 3 blocks per SM (162 registers); ~8 waves of blocks so that the last,
+  // partly filled wave costs little (ncu, C3: 600 blocks = 1.35 waves ran at 55 % of HBM bandwidth)
+  e->cam_chunks = (8 * 3 * e->num_sms + e->M - 1) / e->M;
   if (e->cam_chunks < 1) e->cam_chunks = 1;
   {
     const int64_t per_cam = e->nobs / e->M + 1;
-    const int64_t maxc = per_cam / 256 > 0 ? per_cam / 256 : 1;
+    const int64_t maxc = per_cam / 1024 > 0 ? per_cam / 1024 : 1;  // >= 8 observations per thread
     if (e->cam_chunks > maxc) e->cam_chunks = (int)maxc;
   }
   {
