@@ -460,7 +460,11 @@ static int launch_syrk(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
     BA_LAUNCH_CHECK();
   }
   const int n_tiles = e->syrk_n_tiles;
-  const int slabs = n_tiles >= 4 * e->num_sms ? 1 : (n_tiles >= e->num_sms ? 4 : 8);
+  // enough blocks to fill the GPU (C2: 10 tiles x 8 slabs = 80 blocks took 33 us for 38 MB), at
+  // least one pair of doubles per thread
+  const int slabs_max = TILE * TILE / 2 / 256;
+  int slabs = 1;
+  while (slabs < slabs_max && n_tiles * slabs < 4 * e->num_sms) slabs *= 2;
   syrk_reduce_kernel<TILE><<<dim3(n_tiles, slabs), 256, 0, s>>>(e->Spart, e->syrk_tile_first,
                                                                e->syrk_tile_items, e->P(), e->n_pad,
                                                                e->n_pad, ctl);

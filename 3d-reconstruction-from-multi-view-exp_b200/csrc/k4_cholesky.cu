@@ -217,6 +217,211 @@ chol_update_kernel(double* __restrict__ S, int ld, int n_rows, int c_end, int k0
     }
 }
 
+// ---- small systems: one launch per panel ------------------------------------------------------
+// For n < 2048 the factorisation is a chain of latency-bound launches (C2, n = 451: 8 panels x
+// (panel 17 us + update 12 us) = 0.23 ms of a 0.70 ms solve).  chol_step_kernel takes the trailing
+// update off that chain: launch p runs
+//   * panel blocks   -- as chol_panel_kernel, but each first applies the PREVIOUS panel's update
+//                       to its own 128 x 64 slice (diagonal block + its rows of block column p):
+//                       T -= Lp^T Lp on the FP64 tensor cores, operands staged k-major in shared
+//                       memory next to T (about 2 us), then the elimination;
+//   * update blocks  -- the rest of the previous panel's trailing update (64 x 64 tiles of the
+//                       columns beyond block column p), which nothing in this launch reads.
+// Launch p + 1 needs both, and gets them by stream order.  Lt alternates between two 64-row
+// buffers so the previous panel stays readable while the current one is written.
+__device__ __forceinline__ void step_dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int kSLD = NB + 4;  // k-major operand rows padded to 68 doubles: conflict-free fragment loads
+
+// acc[i][j] += sum_k A[k][row0 + 8 i] B[k][col0 + 8 j] over the 64-deep panel (DMMA fragments)
+template <int FI, int FJ>
+__device__ __forceinline__ void panel_product(const double* __restrict__ A, const double* __restrict__ B,
+                                              int row0, int col0, int kq, double (&acc)[FI][FJ][2]) {
+#pragma unroll 4
+  for (int kk = 0; kk < NB; kk += 4) {
+    double fa[FI], fb[FJ];
+#pragma unroll
+    for (int i = 0; i < FI; ++i) fa[i] = A[(kk + kq) * kSLD + row0 + 8 * i];
+#pragma unroll
+    for (int j = 0; j < FJ; ++j) fb[j] = B[(kk + kq) * kSLD + col0 + 8 * j];
+#pragma unroll
+    for (int i = 0; i < FI; ++i)
+#pragma unroll
+      for (int j = 0; j < FJ; ++j) step_dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+  }
+}
+
+__global__ void __launch_bounds__(kPanelThreads)
+chol_step_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int p_blocks,
+                 double* __restrict__ Lt, const double* __restrict__ Lp, double* __restrict__ W,
+                 ba_lm_state* ctl, int use_ctl) {
+  if (use_ctl && ctl->done) return;
+  extern __shared__ double psm[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  if ((int)blockIdx.x >= p_blocks) {
+    // ---- update block: one 64 x 64 tile of the previous panel's trailing update ---------------
+    double* sA = psm;              // [64][68] Lp[:, r0 ..]
+    double* sB = psm + NB * kSLD;  // [64][68] Lp[:, c0 ..]
+    const int t = blockIdx.x - p_blocks;
+    int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int t0 = k0 + NB;  // first column beyond the block column the panel blocks handle
+    const int r0 = t0 + ti * NB, c0 = t0 + tj * NB;
+    for (int q = tid; q < NB * NB; q += kPanelThreads) {
+      const int m = q >> 6, x = q & 63;
+      sA[m * kSLD + x] = r0 + x < n_rows ? Lp[(size_t)m * ld + r0 + x] : 0.0;
+      sB[m * kSLD + x] = c0 + x < n_rows ? Lp[(size_t)m * ld + c0 + x] : 0.0;
+    }
+    __syncthreads();
+    const int rb = warp >> 2, cb = warp & 3;  // 16 x 16 sub-tile per warp
+    if (ti == tj && cb > rb) return;          // strictly above the diagonal
+    double acc[2][2][2] = {};
+    panel_product<2, 2>(sA, sB, rb * 16 + (lane >> 2), cb * 16 + (lane >> 2), lane & 3, acc);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int r = r0 + rb * 16 + (lane >> 2) + 8 * i, c = c0 + cb * 16 + 2 * (lane & 3) + 8 * j;
+        if (r >= n_rows || c > r) continue;
+        double* dst = S + (size_t)r * ld + c;
+        dst[0] -= acc[i][j][0];
+        if (c + 1 <= r) dst[1] -= acc[i][j][1];
+      }
+    return;
+  }
+  // ---- panel block (see chol_panel_kernel for the elimination) ----------------------------------
+  double(*T)[NB + 1] = reinterpret_cast<double(*)[NB + 1]>(psm);
+  double* col = psm + 2 * NB * (NB + 1);  // [2][128]
+  double* piv = col + 4 * NB;             // [64]
+  double* sB = piv + NB;                  // [64][68] Lp[:, k0 ..]   (previous panel, k-major)
+  double* sA = sB + NB * kSLD;            // [64][68] Lp[:, rbase ..]
+  __shared__ int s_fail;
+  const int rbase = k0 + nb + ((int)blockIdx.x - 1) * NB;
+  if (tid == 0) s_fail = 0;
+  {
+    double vd[8], va[8];
+    const int c = tid & 63;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = (tid >> 6) + 8 * u;
+      vd[u] = (r == c) ? 1.0 : 0.0;
+      if (r < nb && c <= r) vd[u] = S[(size_t)(k0 + r) * ld + k0 + c];
+      va[u] = (blockIdx.x == 0 && r == c) ? 1.0 : 0.0;
+      if (blockIdx.x != 0 && rbase + r < n_rows && c < nb) va[u] = S[(size_t)(rbase + r) * ld + k0 + c];
+    }
+    if (Lp) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int m = (tid >> 6) + 8 * u;
+        sB[m * kSLD + c] = k0 + c < n_rows ? Lp[(size_t)m * ld + k0 + c] : 0.0;
+        sA[m * kSLD + c] = (blockIdx.x != 0 && rbase + c < n_rows) ? Lp[(size_t)m * ld + rbase + c] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = (tid >> 6) + 8 * u;
+      T[r][c] = vd[u];
+      T[NB + r][c] = va[u];
+    }
+  }
+  __syncthreads();
+  if (Lp) {
+    // previous panel's update of this slice: warp -> 16 rows x 32 columns of the 128 x 64 slice
+    const int rb = warp >> 1, ch = warp & 1;
+    const bool own = rb >= 4;  // rows 64..127 = this block's rows, else the diagonal block
+    if (!(own && blockIdx.x == 0)) {
+      double acc[2][4][2] = {};
+      panel_product<2, 4>(own ? sA : sB, sB, (own ? rb - 4 : rb) * 16 + (lane >> 2), ch * 32 + (lane >> 2),
+                          lane & 3, acc);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rl = (own ? rb - 4 : rb) * 16 + (lane >> 2) + 8 * i;  // row inside its 64-block
+          const int c = ch * 32 + 2 * (lane & 3) + 8 * j;
+          const bool row_ok = own ? rbase + rl < n_rows : rl < nb;
+          if (!row_ok) continue;
+          double* dst = &T[(own ? NB : 0) + rl][c];
+          if (c < nb) dst[0] -= acc[i][j][0];
+          if (c + 1 < nb) dst[1] -= acc[i][j][1];
+        }
+    }
+    __syncthreads();
+  }
+  const int r = tid & (2 * NB - 1);
+  const int cg = tid >> 7;
+  double a[kPanelCols];
+#pragma unroll
+  for (int j = 0; j < kPanelCols; ++j) a[j] = T[r][kPanelCols * cg + j];
+  for (int g = 0; g < NB / kPanelCols; ++g) {
+#pragma unroll
+    for (int kk = 0; kk < kPanelCols; ++kk) {
+      const int k = kPanelCols * g + kk;
+      double* ck = col + (kk & 1) * (2 * NB);
+      if (cg == g) ck[r] = a[kk];
+      __syncthreads();
+      if (cg >= g) {
+        const double d = ck[k];
+        if (r == k && cg == g) piv[k] = d;
+        const double la = ck[r] * rcp_newton(d);
+        const double2* pr = reinterpret_cast<const double2*>(ck + kPanelCols * cg);
+        if (cg > g) {
+#pragma unroll
+          for (int jp = 0; jp < kPanelCols / 2; ++jp) {
+            const double2 cv = pr[jp];
+            a[2 * jp] = fma(-la, cv.x, a[2 * jp]);
+            a[2 * jp + 1] = fma(-la, cv.y, a[2 * jp + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int jp = 0; jp < kPanelCols / 2; ++jp) {
+            if (2 * jp + 1 > kk) {
+              const double2 cv = pr[jp];
+              if (2 * jp > kk) a[2 * jp] = fma(-la, cv.x, a[2 * jp]);
+              a[2 * jp + 1] = fma(-la, cv.y, a[2 * jp + 1]);
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kPanelCols; ++j) T[r][kPanelCols * cg + j] = a[j];
+  __syncthreads();
+  if (tid < NB) {
+    const double d = piv[tid];
+    if (tid < nb && !(d > 0.0)) s_fail = 1;
+    piv[tid] = rsqrt(d);
+  }
+  __syncthreads();
+  for (int q = tid; q < 2 * NB * NB; q += kPanelThreads) T[q >> 6][q & 63] *= piv[q & 63];
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    if (tid == 0 && s_fail) ctl->chol_fail = 1;
+    for (int q = tid; q < NB * NB; q += kPanelThreads) {
+      const int m = q >> 6, rr = q & 63;
+      if (m < nb && rr < nb) Lt[(size_t)m * ld + k0 + rr] = rr >= m ? T[rr][m] : 0.0;
+    }
+    for (int q = tid; q < NB * NB; q += kPanelThreads) W[q] = T[NB + (q >> 6)][q & 63];
+  } else {
+    for (int q = tid; q < NB * NB; q += kPanelThreads) {
+      const int rr = q >> 6, c = q & 63;
+      if (rbase + rr < n_rows && c < nb) S[(size_t)(rbase + rr) * ld + k0 + c] = T[NB + rr][c];
+    }
+    for (int q = tid; q < NB * NB; q += kPanelThreads) {
+      const int c = q >> 6, rr = q & 63;
+      if (rbase + rr < n_rows && c < nb) Lt[(size_t)c * ld + rbase + rr] = T[NB + rr][c];
+    }
+  }
+}
+
 // Back substitution L^T x = y (y = row rhs_row of the factor) by 64-column blocks from the
 // last one: rhs_B = y_B - L[below, B]^T x_below (GEMV), x_B = W_B rhs_B with W_B = L_BB^-T from
 // the panel kernel.  One block; x lives in shared memory.
@@ -382,7 +587,32 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
   // FP64 tensor cores (the SYRK kernel of K3 with a subtracting epilogue), which reads and writes
   // S a quarter as often and keeps the DMMA pipe fed from a 3-stage cp.async pipeline.
   static const bool one_level = std::getenv("BA_CHOL_ONE_LEVEL") != nullptr;  // A/B timing only
+  static const bool no_fused = std::getenv("BA_CHOL_NO_FUSED_STEP") != nullptr;  // A/B timing only
   const int OB = (n_rows >= 2048 && !one_level) ? kCholOB : NB;
+  if (OB == NB && !no_fused) {
+    // small systems: one launch per panel, the previous panel's update rides along
+    constexpr size_t kStepSmem = (2 * NB * (NB + 1) + 5 * NB + 2 * NB * kSLD) * sizeof(double);
+    BA_CUDA(cudaFuncSetAttribute(chol_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStepSmem));
+    int panel = 0;
+    for (int k0 = 0; k0 < n; k0 += NB, ++panel) {
+      const int nb = n - k0 < NB ? n - k0 : NB;
+      const int below = n_rows - (k0 + nb);
+      const int p_blocks = 1 + (below + NB - 1) / NB;
+      int u_blocks = 0;
+      if (panel > 0) {
+        const int rest = n_rows - (k0 + NB);  // rows / columns beyond block column `panel`
+        if (rest > 0) {
+          const int nt = (rest + NB - 1) / NB;
+          u_blocks = nt * (nt + 1) / 2;
+        }
+      }
+      double* Lt_cur = e->Lt + (size_t)(panel & 1) * NB * ld;
+      const double* Lt_prev = panel > 0 ? e->Lt + (size_t)((panel - 1) & 1) * NB * ld : nullptr;
+      chol_step_kernel<<<p_blocks + u_blocks, kPanelThreads, kStepSmem, s>>>(
+          e->P(), ld, n_rows, k0, nb, p_blocks, Lt_cur, Lt_prev, e->Winv + (size_t)panel * NB * NB, e->ctl, use_ctl);
+      BA_LAUNCH_CHECK();
+    }
+  } else {
   int panel = 0;
   for (int K0 = 0; K0 < n; K0 += OB) {
     // columns the panels of this block update themselves
@@ -402,6 +632,7 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
     }
     if (OB > NB && K0 + OB < n_rows)  // all four panels of the block are full here
       BA_TRY(launch_chol_wide_update(e->P(), ld, n_rows, K0 + OB, e->Lt, OB, e->ctl, s));
+  }
   }
   if (n >= 2048 && !std::getenv("BA_CHOL_BACKSOLVE_1CTA")) {
     const int nblk = (n + NB - 1) / NB;
