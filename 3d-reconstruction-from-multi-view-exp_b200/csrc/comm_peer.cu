@@ -273,6 +273,7 @@ struct Comm {
 struct HandshakeBlob {
   cudaIpcMemHandle_t handle;
   unsigned long long epoch, epoch_small;
+  unsigned long long fresh;  // 1: this window was allocated by this call (nobody maps it yet)
 };
 static_assert(sizeof(HandshakeBlob) == BA_COMM_HANDLE_BYTES, "handshake blob size");
 
@@ -400,6 +401,7 @@ int ba_comm_create(ba_engine* e, int rank, int world, void* handle_out) {
   BA_CUDA(cudaMemcpy(ep, &c->dev.hdr[rank]->epoch, sizeof(ep), cudaMemcpyDeviceToHost));  // synchronises
   blob.epoch = ep[0];
   blob.epoch_small = ep[1];
+  blob.fresh = c->win->mapped ? 0ull : 1ull;
   std::memcpy(handle_out, &blob, sizeof(blob));
   return BA_OK;
 }

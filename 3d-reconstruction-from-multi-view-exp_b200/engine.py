@@ -68,16 +68,7 @@ class Engine:
     # -- life cycle ---------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
-            comm = getattr(self, "_comm", None)
-            if comm is not None:
-                # unmap the peers' windows, then wait until every rank has done so before this
-                # rank's window is freed (collective: all ranks close their engines together)
-                self._comm = None
-                self._lib.ba_comm_disconnect(self._h)
-                try:
-                    comm[0].barrier(comm[1])
-                except Exception:  # process group already gone (interpreter shutdown)
-                    pass
+            self._comm = None  # exchange windows outlive engines (recycled, never freed)
             self._lib.ba_destroy(self._h)
             self._h = None
 
@@ -219,16 +210,25 @@ class Engine:
         import torch
 
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-        handle = (C.c_ubyte * _cabi.BA_COMM_HANDLE_BYTES)()
+        nb = _cabi.BA_COMM_HANDLE_BYTES
+        handle = (C.c_ubyte * nb)()
         _cabi.check(self._lib.ba_comm_create(self._h, rank, world, handle))
         on_gpu = str(dist.get_backend(group)) == "nccl"
         dev = f"cuda:{self.device}" if on_gpu else "cpu"
-        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=dev)
-        gathered = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine, group=group)
-        blob = b"".join(t.cpu().numpy().tobytes() for t in gathered)
+        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
+        if on_gpu:
+            gathered = torch.empty(world * nb, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(gathered, mine, group=group)
+            blob = gathered.cpu().numpy().tobytes()
+        else:
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine, group=group)
+            blob = b"".join(t.numpy().tobytes() for t in parts)
         _cabi.check(self._lib.ba_comm_connect(self._h, blob))
-        dist.barrier(group)  # nobody stores into a window before every rank has mapped them all
+        # a new window must be mapped by every rank before anybody stores into it; recycled
+        # windows (the usual case after the first engine of a shape) are mapped already
+        if any(blob[r * nb + nb - 8] for r in range(world)):
+            dist.barrier(group)
         self._comm = (dist, group)
 
     def comm_size(self) -> int:

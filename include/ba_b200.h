@@ -178,20 +178,22 @@ int ba_cost_buffer(ba_engine* e, void** device_ptr, int64_t* n_doubles);
 /* The reference is a single process (no parallelism of any kind); these
  * calls are the multi-GPU form of the sums at :135-143 and :674-676.  ba_comm_create allocates
  * this rank's exchange window (header + reduce buffer + one staging slot per rank), moves the
- * reduce buffer into it and returns an opaque blob (the window's CUDA IPC handle and its exchange
- * epochs, BA_COMM_HANDLE_BYTES bytes).  Windows are kept for the life of the process and handed to
+ * reduce buffer into it and returns an opaque blob (the window's CUDA IPC handle, its exchange
+ * epochs and, in the last 8 bytes, 1 if the window is new / 0 if it is a recycled one that the
+ * peers already map; BA_COMM_HANDLE_BYTES bytes).  Windows are kept for the life of the process and handed to
  * the next engine of the same shape, mappings included.
  * The host gathers the handles of all ranks in rank order (any transport; e.g.
- * torch.distributed.all_gather) and passes them to ba_comm_connect, then synchronises the ranks
- * once.  From then on ba_lm_begin / ba_lm_phase_* / ba_lm_iterate / ba_lm_run sum the partial
+ * torch.distributed.all_gather) and passes them to ba_comm_connect, then -- if any window is
+ * new -- synchronises the ranks once (nobody may store into a window that is not mapped
+ * everywhere yet).  From then on ba_lm_begin / ba_lm_phase_* / ba_lm_iterate / ba_lm_run sum the partial
  * reduced system and the costs over all ranks with the library's own kernels (peer stores,
  * deterministic rank-order addition); the host must NOT all-reduce the buffers as well. */
-#define BA_COMM_HANDLE_BYTES 80
+#define BA_COMM_HANDLE_BYTES 88
 int ba_comm_create(ba_engine* e, int rank, int world, void* handle_out);
 int ba_comm_connect(ba_engine* e, const void* handles /* world x BA_COMM_HANDLE_BYTES */);
-/* Quiesce this engine's side of the exchange (drains its streams).  Every rank calls this and the
- * host synchronises the ranks before the engines are destroyed, so that no rank starts the next
- * engine's exchange on a recycled window while another is still inside the previous run. */
+/* Quiesce this engine's side of the exchange (drains its streams).  Optional: ba_destroy does the
+ * same.  No rank-wide synchronisation is needed around destruction -- windows are never freed, and
+ * an exchange can only start on a recycled window after every peer has left the previous one. */
 int ba_comm_disconnect(ba_engine* e);
 int ba_comm_world(ba_engine* e, int* rank, int* world);
 
