@@ -320,3 +320,82 @@ def test_shadow_module_intercepts_reference_import(ba):
         for k in [k for k in sys.modules if k == "lib" or k.startswith("lib.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def _oracle_run(x, vis, X0, K0, R0, t0, axis, f0, max_iter):
+    ora = O.OracleBundleAdjuster(x, X0, K0, R0, t0, f0=f0, visibility_index=vis, axis=axis)
+    out = ora.optimize(2.0, 1e-8, max_iter=max_iter, verbose=False)
+    return np.array([r["E"] for r in ora.trace]), out
+
+
+def test_minimal_problem_two_cameras(ba):
+    """Smallest admissible scene: 2 cameras (9 * 2 - 7 = 11 unknowns in one partial Cholesky panel),
+    12 points; the whole run against the oracle."""
+    sc = ba.scenes.make_scene(2, 12, seed=21, visibility=1.0)
+    x, vis = sc.dense_x()
+    adj = ba.BundleAdjuster(x, sc.X0, sc.K0, sc.R0, sc.t0, f0=sc.f0, axis=sc.axis)
+    with contextlib.redirect_stdout(io.StringIO()):
+        X, K, R, t = adj.optimize(2.0, 1e-8, max_iter=30)
+    E = np.array([adj.records[0]["E_prev"]] + [r["E"] for r in adj.records])
+    Eo, (Xo, Ko, Ro, to) = _oracle_run(x, None, sc.X0, sc.K0, sc.R0, sc.t0, sc.axis, sc.f0, 30)
+    assert E.shape == Eo.shape
+    np.testing.assert_allclose(E, Eo, rtol=1e-8)
+    np.testing.assert_allclose(X, Xo, atol=1e-5)
+    np.testing.assert_allclose(K, Ko, atol=1e-5)
+
+
+def test_point_with_a_single_view_is_not_an_error(ba):
+    """SURVEY.md 8b [probe]: a point seen once gives a rank-2 V_j that the reference does not
+    detect (multiplicative damping makes it invertible); the run proceeds.  Same here, with the
+    same first costs as the oracle."""
+    g = load_golden("small_sparse_xup")
+    x, vis, X0, K0, R0, t0, axis, f0 = case_inputs(g)
+    vis2 = vis.copy()
+    vis2[5, :] = False
+    vis2[5, 2] = True
+    adj = ba.BundleAdjuster(x, X0, K0, R0, t0, visibility_index=vis2, axis=axis)
+    with contextlib.redirect_stdout(io.StringIO()):
+        adj.optimize(2.0, 1e-8, max_iter=3)
+    E = np.array([adj.records[0]["E_prev"]] + [r["E"] for r in adj.records])
+    Eo, _ = _oracle_run(x, vis2, X0, K0, R0, t0, axis, f0, 3)
+    np.testing.assert_allclose(E, Eo[: len(E)], rtol=1e-7)
+
+
+def test_retry_cap_raises_instead_of_looping_forever(ba):
+    """Documented deviation (3): the reference's inner loop has no bound (:118).  Config 1's very
+    first Gauss-Newton step is rejected (E 66.3 -> 3466 at c = 1e-4); with scale_factor = 1 the
+    damping never grows, so the reference would repeat that solve forever.  The engine stops after
+    max_retries solves with RuntimeError, and the state is left at the initial one."""
+    g = load_golden("c1_euclid")
+    x, vis, X0, K0, R0, t0, axis, f0 = case_inputs(g)
+    adj = ba.BundleAdjuster(x, X0, K0, R0, t0, visibility_index=vis, axis=axis, max_retries=5)
+    with pytest.raises(RuntimeError, match="retries"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            adj.optimize(1.0, 1e-8, max_iter=10)
+    st = adj.engine.lm_state()
+    assert st.count == 0 and st.solves == 5 and st.E == pytest.approx(float(g["E"][0]), rel=1e-9)
+
+
+def test_c_abi_rejects_bad_arguments(ba):
+    import ctypes as C
+
+    cabi = ba.submodule("_cabi")
+    lib = cabi.load()
+    h = C.c_void_p()
+    for kwargs in (dict(n_cams=1), dict(n_points=0), dict(axis=7), dict(f0=0.0), dict(device=99)):
+        base = dict(n_points=10, n_obs=40, n_cams=4, axis=1, f0=1.0, dense=1, device=0)
+        base.update(kwargs)
+        if "n_points" in kwargs or "n_cams" in kwargs:
+            base["n_obs"] = base["n_points"] * base["n_cams"]
+        prob = cabi.Problem(base["n_points"], max(base["n_obs"], 0), base["n_cams"], base["axis"], base["f0"],
+                            base["dense"], base["device"])
+        assert lib.ba_create(C.byref(prob), C.byref(h)) == cabi.BA_ERR_INVALID
+        assert lib.ba_last_error()
+    # dense problem whose observation count does not match
+    prob = cabi.Problem(10, 39, 4, 1, 1.0, 1, 0)
+    assert lib.ba_create(C.byref(prob), C.byref(h)) == cabi.BA_ERR_INVALID
+    # calls out of order
+    eng = ba.Engine(10, 4, 40, 1.0, "x-up_z-forward", True)
+    with pytest.raises(RuntimeError):
+        eng.lm_begin(2.0, 1e-8, 10)
+    eng.close()
