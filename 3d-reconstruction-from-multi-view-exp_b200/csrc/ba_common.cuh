@@ -45,6 +45,7 @@ constexpr int kPT = 12;       // doubles per point in the pair kernel's point ta
                               // X (3), damped V^-1 (00 01 02 11 12 22), 3 pad = 96 B = 3 sectors
 constexpr int kCholNB = 64;   // panel width of the blocked Cholesky
 constexpr int kCholOB = 256;  // outer block (4 panels) of the two-level variant for large systems
+constexpr int kCholSplitMinRows = 2560;  // trailing rows from which the rank-256 update runs on 128-tiles
 constexpr int kMaxRecords = 4096;
 constexpr int kMaxRanks = 8;    // ranks of one peer-memory exchange (one NVSwitch domain)
 
@@ -261,8 +262,19 @@ int syrk_plan_selftest(int n_cams, int64_t n_points, int tile, int num_sms, int*
                        double* makespan_rows, double* ideal_rows);
 int launch_assemble(ba_engine* e, bool conditional, double c_host, cudaStream_t s);
 int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s);
+// How the rank-256 trailing updates of a sharded run's (replicated) Cholesky are divided over
+// the ranks: tile row g of the global 128-tile grid belongs to rank g % world; the owner updates
+// its tiles only and stores those within `push_cols` columns of the update's origin -- the next
+// block column, which every rank's panels read -- into every rank's S over NVLink.
+struct CholSplit {
+  int rank = 0, world = 1;  // world == 1: every rank updates everything (no split)
+  int push_cols = 0;
+  double* S_peer[kMaxRanks] = {};
+};
 int launch_chol_wide_update(double* S, int ld, int n_rows, int t0, const double* Lt, int depth,
-                            const ba_lm_state* ctl, cudaStream_t s);
+                            const ba_lm_state* ctl, cudaStream_t s, const CholSplit* split);
+void comm_chol_split(ba_engine* e, CholSplit* out);
+int launch_comm_chol_sync(ba_engine* e, bool conditional, cudaStream_t s);
 int launch_update_trial(ba_engine* e, bool conditional, cudaStream_t s);
 int launch_decide(ba_engine* e, cudaStream_t s);
 int launch_lm_begin(ba_engine* e, double scale, double tol, int max_iter, int max_retries,

@@ -47,6 +47,8 @@ struct CommHeader {
   unsigned long long flag_bcast[kMaxRanks];     // [owner] owner's sums have landed in my red
   unsigned long long flag_small[2][kMaxRanks];  // [parity][src]
   double small[2][kMaxRanks][2];                // [parity][src] (cost, singular flag)
+  unsigned long long flag_chol[kMaxRanks];      // [src]   src has finished its share of a trailing update
+  unsigned long long epoch_chol;                // completed trailing-update exchanges (local)
   unsigned long long epoch;                     // completed sums of red (local)
   unsigned long long epoch_small;               // completed small sums (local)
   unsigned int count_push, count_reduce;        // last-CTA-done counters (local)
@@ -241,6 +243,28 @@ __global__ void comm_small_kernel(CommDev cd, double* cost_buf, int slot, ba_lm_
   }
 }
 
+// Closes one divided trailing update of the Cholesky (k4_cholesky.cu): everything this rank stored
+// into the peers' matrices in the preceding kernel is published, and the peers' shares are awaited.
+__global__ void comm_chol_sync_kernel(CommDev cd, ba_lm_state* ctl, int use_ctl) {
+  if (use_ctl && ctl->done) return;
+  CommHeader* me = cd.hdr[cd.rank];
+  const unsigned long long epoch = me->epoch_chol + 1;
+  const int t = threadIdx.x;
+  __shared__ int s_ok;
+  if (t == 0) s_ok = 1;
+  __syncthreads();
+  if (t < cd.world && t != cd.rank) {
+    __threadfence_system();
+    st_release_sys(&cd.hdr[t]->flag_chol[cd.rank], epoch);
+    if (!spin_until(&me->flag_chol[t], epoch)) s_ok = 0;
+  }
+  __syncthreads();
+  if (t == 0) {
+    if (!s_ok) comm_fail(ctl);
+    me->epoch_chol = epoch;
+  }
+}
+
 // ---- host side --------------------------------------------------------------------------------
 static inline int64_t round_up_i64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
@@ -299,6 +323,23 @@ int launch_comm_allreduce_cost(ba_engine* e, int slot, bool conditional, cudaStr
   if (!c || !c->connected) { set_error("exchange window not connected"); return BA_ERR_STATE; }
   ProfScope ps(e, PG_COMM, s);
   comm_small_kernel<<<1, 32, 0, s>>>(c->dev, e->cost_buf, slot, e->ctl, conditional ? 1 : 0);
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}
+
+void comm_chol_split(ba_engine* e, CholSplit* out) {
+  *out = CholSplit();
+  const Comm* c = e->comm;
+  if (!c || !c->connected) return;
+  out->rank = c->dev.rank;
+  out->world = c->dev.world;
+  for (int q = 0; q < c->dev.world; ++q) out->S_peer[q] = c->dev.red[q];
+}
+
+int launch_comm_chol_sync(ba_engine* e, bool conditional, cudaStream_t s) {
+  Comm* c = e->comm;
+  if (!c || !c->connected) { set_error("exchange window not connected"); return BA_ERR_STATE; }
+  comm_chol_sync_kernel<<<1, 32, 0, s>>>(c->dev, e->ctl, conditional ? 1 : 0);
   BA_LAUNCH_CHECK();
   return BA_OK;
 }

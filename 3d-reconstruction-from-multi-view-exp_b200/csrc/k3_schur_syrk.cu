@@ -55,6 +55,14 @@ __device__ __forceinline__ void tile_from_linear(int t, int& ti, int& tj) {
   tj = t - ti * (ti + 1) / 2;
 }
 
+// Division of a trailing update over the ranks of a sharded run (see CholSplit): the CTA of a tile
+// row this rank does not own exits at once; tiles that start within push_cols columns are also
+// stored into every other rank's matrix (peer[q] = that rank's S at the update's origin).
+struct SubSplit {
+  int rank, world, tile_row0, push_cols;
+  double* peer[kMaxRanks];
+};
+
 // TILE x TILE output tile per CTA; WR x WC warps, each owning a (TILE/WR) x (TILE/WC) sub-tile.
 // SUB = false: the tile of this split is written to part[split][tile] (Schur product).
 // SUB = true:  one split; the tile is subtracted in place from the lower triangle of the n_store x
@@ -64,7 +72,7 @@ template <int TILE, int WR, int WC, int KC, bool SUB>
 __global__ void __launch_bounds__(WR* WC * 32)
 syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_chunks,
                  const SyrkItem* __restrict__ items, double* __restrict__ part,
-                 const ba_lm_state* ctl, int n_store) {
+                 const ba_lm_state* ctl, int n_store, SubSplit sp) {
   if (ctl && ctl->done) return;
   constexpr int NT = WR * WC * 32;
   constexpr int LDS = TILE + 4;
@@ -81,6 +89,7 @@ syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_c
   int64_t c_lo, c_hi;
   if (SUB) {
     tile_from_linear(blockIdx.x, ti, tj);
+    if (sp.world > 1 && (sp.tile_row0 + ti) % sp.world != sp.rank) return;  // another rank's tile row
     c_lo = 0;
     c_hi = n_chunks;
   } else {
@@ -211,14 +220,23 @@ syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_c
       for (int j = 0; j < FN; ++j) {
         const int r = ti * TILE + orow + 8 * i, c = tj * TILE + ocol + 8 * j;
         if (r >= n_store || c > r) continue;
-        double* p = part + (size_t)r * ld + c;
+        const size_t off = (size_t)r * ld + c;
+        double* p = part + off;
+        const bool push = sp.world > 1 && tj * TILE < sp.push_cols;
         if (c + 1 <= r) {
           double2 v = *reinterpret_cast<double2*>(p);
           v.x -= acc[i][j][0];
           v.y -= acc[i][j][1];
           *reinterpret_cast<double2*>(p) = v;
+          if (push)
+            for (int q = 0; q < sp.world; ++q)
+              if (q != sp.rank) *reinterpret_cast<double2*>(sp.peer[q] + off) = v;
         } else {
-          *p -= acc[i][j][0];
+          const double v = *p - acc[i][j][0];
+          *p = v;
+          if (push)
+            for (int q = 0; q < sp.world; ++q)
+              if (q != sp.rank) sp.peer[q][off] = v;
         }
       }
     return;
@@ -456,7 +474,7 @@ static int launch_syrk(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
   {
     ProfScope ps(e, PG_SYRK, s);
     syrk_dmma_kernel<TILE, WR, WC, KC, false><<<e->syrk_n_items, WR * WC * 32, smem, s>>>(
-        e->Yt, e->n_pad, e->n_pad, n_chunks, e->syrk_items, e->Spart, ctl, 0);
+        e->Yt, e->n_pad, e->n_pad, n_chunks, e->syrk_items, e->Spart, ctl, 0, SubSplit{0, 1, 0, 0, {}});
     BA_LAUNCH_CHECK();
   }
   const int n_tiles = e->syrk_n_tiles;
@@ -476,7 +494,7 @@ static int launch_syrk(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
 // [depth][ld]: the wide trailing update of the two-level blocked Cholesky.
 template <int TILE, int WR, int WC, int KC>
 static int launch_syrk_sub(double* S, int ld, int n_rows, int t0, const double* Lt, int depth,
-                           const ba_lm_state* ctl, cudaStream_t s) {
+                           const ba_lm_state* ctl, cudaStream_t s, const CholSplit* split) {
   const int n_store = n_rows - t0;
   const int n_valid = (n_store + 7) / 8 * 8;  // <= ld - t0: ld is a multiple of 8, t0 of 64
   const int nt1 = (n_valid + TILE - 1) / TILE;
@@ -485,17 +503,28 @@ static int launch_syrk_sub(double* S, int ld, int n_rows, int t0, const double* 
   const size_t smem = (size_t)2 * kStages * KC * (TILE + 4) * sizeof(double);
   BA_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<TILE, WR, WC, KC, true>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t origin = (size_t)t0 * ld + t0;
+  SubSplit sp{0, 1, 0, 0, {}};
+  if (split && split->world > 1) {
+    sp.rank = split->rank;
+    sp.world = split->world;
+    sp.tile_row0 = t0 / TILE;
+    sp.push_cols = split->push_cols;
+    for (int q = 0; q < split->world; ++q) sp.peer[q] = split->S_peer[q] + origin;
+  }
   syrk_dmma_kernel<TILE, WR, WC, KC, true><<<n_tiles, WR * WC * 32, smem, s>>>(
-      Lt + t0, ld, n_valid, n_chunks, nullptr, S + (size_t)t0 * ld + t0, ctl, n_store);
+      Lt + t0, ld, n_valid, n_chunks, nullptr, S + origin, ctl, n_store, sp);
   BA_LAUNCH_CHECK();
   return BA_OK;
 }
 
+// 128-tiles (one CTA per SM) once there are enough of them, 64-tiles (four per SM) below.  Only
+// the 128-tile form is divided over the ranks of a sharded run.
 int launch_chol_wide_update(double* S, int ld, int n_rows, int t0, const double* Lt, int depth,
-                            const ba_lm_state* ctl, cudaStream_t s) {
-  // 128-tiles (one CTA per SM) once there are enough of them, 64-tiles (four per SM) below
-  if (n_rows - t0 >= 2560) return launch_syrk_sub<128, 4, 4, 32>(S, ld, n_rows, t0, Lt, depth, ctl, s);
-  return launch_syrk_sub<64, 2, 2, 16>(S, ld, n_rows, t0, Lt, depth, ctl, s);
+                            const ba_lm_state* ctl, cudaStream_t s, const CholSplit* split) {
+  if (n_rows - t0 >= kCholSplitMinRows)
+    return launch_syrk_sub<128, 4, 4, 32>(S, ld, n_rows, t0, Lt, depth, ctl, s, split);
+  return launch_syrk_sub<64, 2, 2, 16>(S, ld, n_rows, t0, Lt, depth, ctl, s, nullptr);
 }
 
 int launch_k3(ba_engine* e, bool conditional, cudaStream_t s) {

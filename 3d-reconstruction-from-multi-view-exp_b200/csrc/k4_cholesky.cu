@@ -589,6 +589,9 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
   static const bool one_level = std::getenv("BA_CHOL_ONE_LEVEL") != nullptr;  // A/B timing only
   static const bool no_fused = std::getenv("BA_CHOL_NO_FUSED_STEP") != nullptr;  // A/B timing only
   const int OB = (n_rows >= 2048 && !one_level) ? kCholOB : NB;
+  CholSplit split;
+  comm_chol_split(e, &split);
+  if (std::getenv("BA_CHOL_NO_SPLIT")) split.world = 1;  // A/B timing only (set on every rank)
   if (OB == NB && !no_fused) {
     // small systems: one launch per panel, the previous panel's update rides along
     constexpr size_t kStepSmem = (2 * NB * (NB + 1) + 5 * NB + 2 * NB * kSLD) * sizeof(double);
@@ -630,8 +633,20 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
       chol_update_kernel<<<grid, 256, kUpdateSmem, s>>>(e->P(), ld, n_rows, c_end, k0, nb, Lt, e->ctl, use_ctl);
       BA_LAUNCH_CHECK();
     }
-    if (OB > NB && K0 + OB < n_rows)  // all four panels of the block are full here
-      BA_TRY(launch_chol_wide_update(e->P(), ld, n_rows, K0 + OB, e->Lt, OB, e->ctl, s));
+    if (OB > NB && K0 + OB < n_rows) {  // all four panels of the block are full here
+      const int t0 = K0 + OB, remaining = n_rows - t0;
+      if (split.world > 1 && remaining >= kCholSplitMinRows) {
+        // sharded run: every rank updates its own tile rows and sends the part the next panels
+        // read -- the next block column, or everything that is left when the following update
+        // will not be divided any more -- to all ranks; one flag exchange closes the step
+        const bool next_divided = t0 + OB < n_rows && n_rows - (t0 + OB) >= kCholSplitMinRows;
+        split.push_cols = next_divided ? OB : (remaining + 127) / 128 * 128;
+        BA_TRY(launch_chol_wide_update(e->P(), ld, n_rows, t0, e->Lt, OB, e->ctl, s, &split));
+        BA_TRY(launch_comm_chol_sync(e, conditional, s));
+      } else {
+        BA_TRY(launch_chol_wide_update(e->P(), ld, n_rows, t0, e->Lt, OB, e->ctl, s, nullptr));
+      }
+    }
   }
   }
   if (n >= 2048 && !std::getenv("BA_CHOL_BACKSOLVE_1CTA")) {

@@ -98,3 +98,65 @@ def test_two_ranks_match_reference(tmp_path, case, exchange):
     # only rank 0 prints the reference's iteration lines; its debug log has one entry per state
     assert int(out[0]["lines"]) == len(g["E"]) - 1 and int(out[1]["lines"]) == 0
     assert int(out[0]["nlog"]) == len(g["E"])
+
+
+def _worker_large(rank, world, port, out_dir, per_rank_gpu):
+    import contextlib
+    import io
+
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev = rank if per_rank_gpu else 0
+    torch.cuda.set_device(dev)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, ROOT)
+        import ba_b200
+
+        sharded = ba_b200.submodule("sharded")
+        sc = ba_b200.scenes.make_scene(320, 450, seed=7, visibility=0.3)
+        lo, hi = sharded.shard_bounds(sc.n_points, world, sc.obs_ptr)[rank]
+        a, b = int(sc.obs_ptr[lo]), int(sc.obs_ptr[hi])
+        adj = ba_b200.BundleAdjuster.from_observations(
+            sc.obs_ptr[lo:hi + 1] - sc.obs_ptr[lo], sc.obs_cam[a:b], sc.obs_xy[a:b], sc.X0[lo:hi], sc.K0,
+            sc.R0, sc.t0, f0=sc.f0, axis=sc.axis, device=dev, process_group=dist.group.WORLD, exchange="peer")
+        with contextlib.redirect_stdout(io.StringIO()):
+            X, K, R, t = adj.optimize(2.0, 1e-8, max_iter=3)
+        E = np.array([adj.records[0]["E_prev"]] + [r["E"] for r in adj.records])
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), E=E, K=K, R=R, t=t)
+        adj.engine.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_divided_cholesky_of_a_large_reduced_system(tmp_path):
+    """320 cameras (n = 2880): the reduced system is factored by the two-level Cholesky whose first
+    rank-256 trailing update is divided over the two ranks (each updates its own 128-tile rows and
+    stores the next block column into the other rank's matrix over peer memory).  Three iterations
+    against the CPU oracle on the whole scene; both ranks must hold identical cameras."""
+    import torch
+    import torch.multiprocessing as mp
+
+    import ba_b200
+    from oracle import ba_oracle as O
+
+    world = 2
+    per_rank_gpu = torch.cuda.device_count() >= world
+    mp.spawn(_worker_large, args=(world, _free_port(), str(tmp_path), per_rank_gpu), nprocs=world, join=True)
+    out = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
+    sc = ba_b200.scenes.make_scene(320, 450, seed=7, visibility=0.3)
+    obs = O.ObsList(sc.n_points, sc.n_cams, np.repeat(np.arange(sc.n_points), np.diff(sc.obs_ptr)),
+                    sc.obs_cam.astype(np.int64), sc.obs_xy, sc.obs_ptr)
+    ora = O.OracleBundleAdjuster(None, sc.X0, sc.K0, sc.R0, sc.t0, f0=sc.f0, axis=sc.axis, obs=obs)
+    Xo, Ko, Ro, to = ora.optimize(2.0, 1e-8, max_iter=3, verbose=False)
+    Eo = np.array([r["E"] for r in ora.trace])
+    for o in out:
+        assert o["E"].shape == Eo.shape
+        np.testing.assert_allclose(o["E"], Eo, rtol=1e-9)
+        np.testing.assert_allclose(o["K"], Ko, atol=1e-6)
+        np.testing.assert_allclose(o["R"], Ro, atol=1e-6)
+        np.testing.assert_allclose(o["t"], to, atol=1e-6)
+    assert np.array_equal(out[0]["R"], out[1]["R"]) and np.array_equal(out[0]["t"], out[1]["t"])
