@@ -30,6 +30,7 @@
 // Flags are monotone 64-bit epochs written with st.release.sys after a system-scope fence and
 // polled with ld.acquire.sys; staged data is read with ld.global.cg (L2 only).  Every spin has a
 // wall-clock limit: a missing peer turns into BA_ERR_COMM instead of a hung GPU.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -40,7 +41,7 @@
 namespace ba {
 
 constexpr int kSegBlock = 4;  // consecutive segments dealt to one rank
-constexpr unsigned long long kSpinLimitNs = 30ull * 1000000000ull;
+__device__ unsigned long long g_spin_limit_ns = 30ull * 1000000000ull;  // BA_COMM_SPIN_LIMIT_S overrides
 
 struct CommHeader {
   unsigned long long flag_push[kMaxRanks];      // [src]   src's copies for me have landed
@@ -85,7 +86,7 @@ __device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsig
   const unsigned long long t0 = global_ns();
   while (ld_acquire_sys(flag) < want) {
     __nanosleep(64);
-    if (global_ns() - t0 > kSpinLimitNs) return false;
+    if (global_ns() - t0 > g_spin_limit_ns) return false;
   }
   return true;
 }
@@ -372,6 +373,10 @@ static int comm_create(ba_engine* e, int rank, int world) {
     return BA_ERR_INVALID;
   }
   BA_CUDA(cudaSetDevice(e->device));
+  if (const char* lim = std::getenv("BA_COMM_SPIN_LIMIT_S")) {
+    const unsigned long long ns = (unsigned long long)(std::atof(lim) * 1e9);
+    if (ns > 0) BA_CUDA(cudaMemcpyToSymbol(g_spin_limit_ns, &ns, sizeof(ns)));
+  }
   Comm* c = new (std::nothrow) Comm();
   if (!c) { set_error("out of host memory"); return BA_ERR_CUDA; }
   c->dev.rank = rank;

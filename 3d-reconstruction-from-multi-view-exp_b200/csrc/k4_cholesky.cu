@@ -641,6 +641,11 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
         // will not be divided any more -- to all ranks; one flag exchange closes the step
         const bool next_divided = t0 + OB < n_rows && n_rows - (t0 + OB) >= kCholSplitMinRows;
         split.push_cols = next_divided ? OB : (remaining + 127) / 128 * 128;
+        // Before the FIRST divided update nothing has ordered the ranks since the sum of `red`:
+        // a rank that is ahead would store into a peer's matrix while that peer is still
+        // assembling it in place.  One more flag exchange closes the window (the later steps are
+        // ordered by the exchange that ends the step before).
+        if (K0 == 0) BA_TRY(launch_comm_chol_sync(e, conditional, s));
         BA_TRY(launch_chol_wide_update(e->P(), ld, n_rows, t0, e->Lt, OB, e->ctl, s, &split));
         BA_TRY(launch_comm_chol_sync(e, conditional, s));
       } else {
