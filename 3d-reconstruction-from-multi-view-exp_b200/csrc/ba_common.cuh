@@ -249,6 +249,16 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
 }
 #endif
 
+// Grid of a kernel whose blocks loop over `items` work units with a stride of the grid: at most
+// `cap` blocks, and every block gets the same number of units (to within one) -- with the plain
+// min(items, cap) a count just above the cap gives a few blocks two units and everybody else one,
+// i.e. a second pass at a few percent occupancy (C2: 1250 point groups on 1184 blocks).
+inline int balanced_blocks(int64_t items, int64_t cap) {
+  if (items <= cap) return (int)(items > 0 ? items : 1);
+  const int64_t rounds = (items + cap - 1) / cap;
+  return (int)((items + rounds - 1) / rounds);
+}
+
 // kernel launchers implemented in the .cu files (each returns a ba_status)
 int launch_cam_prep(ba_engine* e, int which, cudaStream_t s);
 int launch_cost(ba_engine* e, int which, int slot, cudaStream_t s);

@@ -64,9 +64,7 @@ k2a_point_blocks_kernel(int64_t N, int M, const int64_t* __restrict__ obs_ptr,
 
 int launch_k2a(ba_engine* e, cudaStream_t s, bool conditional) {
   const ba_lm_state* ctl = conditional ? e->ctl : nullptr;
-  int64_t blocks = (e->N + 7) / 8;  // 8 warps per block
-  const int64_t cap = (int64_t)e->num_sms * 16;
-  const int grid = (int)(blocks < cap ? blocks : cap);
+  const int grid = balanced_blocks((e->N + 7) / 8, (int64_t)e->num_sms * 16);  // 8 warps per block
   if (e->dense)
     k2a_point_blocks_kernel<true><<<grid, 256, 0, s>>>(e->N, e->M, e->obs_ptr, e->JP, e->V, e->GPT, ctl);
   else
@@ -320,9 +318,7 @@ int launch_k2b(ba_engine* e, bool conditional, double c_host, cudaStream_t s) {
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStage));
   BA_CUDA(cudaFuncSetAttribute(k2b_point_solve_kernel<false>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStage));
-  int64_t blocks = (e->N + 7) / 8;
-  const int64_t cap = (int64_t)e->num_sms * 16;
-  const int grid = (int)(blocks < cap ? blocks : cap);
+  const int grid = balanced_blocks((e->N + 7) / 8, (int64_t)e->num_sms * 16);
   if (e->dense)
     k2b_point_solve_kernel<true><<<grid, 256, kStage, s>>>(
         e->N, e->M, e->axis, e->obs_ptr, e->obs_cam, e->JP, e->JC, e->V, e->GPT, c_host, e->ctl,

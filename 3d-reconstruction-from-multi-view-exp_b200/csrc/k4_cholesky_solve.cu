@@ -193,9 +193,7 @@ int launch_update_trial(ba_engine* e, bool conditional, cudaStream_t s) {
                                                            c1.f, c1.u, c1.R, c1.t, e->camtab[1],
                                                            e->ctl, use_ctl);
   BA_LAUNCH_CHECK();
-  int64_t blocks = (e->N + 7) / 8;
-  const int64_t cap = (int64_t)e->num_sms * 8;
-  const int grid = (int)(blocks < cap ? blocks : cap);
+  const int grid = balanced_blocks((e->N + 7) / 8, (int64_t)e->num_sms * 8);  // 8 warps = 8 points per block
   const double2* xy = reinterpret_cast<const double2*>(e->obs_xy);
   if (e->dense)
     point_update_cost_kernel<true><<<grid, 256, 0, s>>>(
