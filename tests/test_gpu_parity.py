@@ -133,6 +133,8 @@ def test_kernels_match_oracle_on_golden_cases(ba, name):
     (5, 9000, 0.7, "x-up_z-forward"),       # sparse path, few cameras, several bitmap batches per pair
     (320, 450, 0.3, "x-up_z-forward"),      # n = 2880: two-level Cholesky (rank-256 DMMA updates, 128- and 64-tiles), grid-wide back substitution
     (260, 300, 1.0, "x-right_z-forward"),   # n = 2340, dense: same with 64-tiles only, edge tiles cut by n_rows
+    (1000, 1500, 0.1, "x-up_z-forward"),    # C4's camera count: n = 8993, 35 outer blocks of the two-level Cholesky,
+                                            # 141-CTA back substitution, 31 x 31 pair tiles (oracle: ~25 s of LU)
 ])
 def test_kernels_match_oracle_on_random_scenes(ba, n_cams, n_points, visibility, axis):
     sc = ba.scenes.make_scene(n_cams, n_points, seed=n_cams, visibility=visibility, axis=axis)
@@ -302,6 +304,67 @@ def test_full_size_c2_properties(ba):
     nX2, nR2, nt2 = O.normalize_gauge(X2, R2, t2, sc.axis)
     np.testing.assert_allclose(np.abs(nX2), np.abs(nX), rtol=0, atol=1e-5)
     np.testing.assert_allclose(np.abs(nt2), np.abs(nt), rtol=0, atol=1e-5)
+
+
+def test_full_size_c3_properties(ba):
+    """Config 3 (200 cameras x 100k points, dense: 2e7 observations, n = 1793) at full size.  The
+    oracle needs ~45 s per iteration here, so the run is checked through properties: the cost the
+    engine reports equals the oracle's cost function evaluated on the returned state (initial and
+    final), the cost is additive over point shards (two half-scene engines), it decreases
+    monotonically, and the converged RMS sits at the injected noise level."""
+    sc = ba.scenes.make_scene(**ba.scenes.CONFIGS["c3"])
+    N, M = sc.n_points, sc.n_cams
+    obs = O.ObsList(N, M, np.repeat(np.arange(N), M), np.tile(np.arange(M), N), sc.obs_xy, sc.obs_ptr)
+    adj = ba.BundleAdjuster.from_observations(sc.obs_ptr, None, sc.obs_xy, sc.X0, sc.K0, sc.R0, sc.t0,
+                                              f0=sc.f0, axis=sc.axis, dense=True)
+    # initial cost: engine vs oracle on the normalised state, and additivity over two shards
+    Xn, Rn, tn = O.normalize_gauge(sc.X0, sc.R0, sc.t0, sc.axis)
+    f, u = sc.K0[:, 0, 0].copy(), sc.K0[:, :2, 2].copy()
+    E0 = adj.engine.cost(0)
+    assert E0 == pytest.approx(O.cost(obs, Xn, f, u, Rn, tn, sc.f0), rel=1e-12)
+    h = N // 2
+    parts = []
+    for lo, hi in ((0, h), (h, N)):
+        eng = ba.Engine(hi - lo, M, (hi - lo) * M, sc.f0, sc.axis, True)
+        eng.set_observations(None, None, sc.obs_xy[lo * M: hi * M])
+        eng.set_state(Xn[lo:hi], Rn, tn, f, u)
+        parts.append(eng.cost(0))
+        eng.close()
+    assert parts[0] + parts[1] == pytest.approx(E0, rel=1e-12)
+    with contextlib.redirect_stdout(io.StringIO()):
+        X, K, R, t = adj.optimize(2.0, 1e-8, max_iter=100)
+    E = np.array([adj.records[0]["E_prev"]] + [r["E"] for r in adj.records])
+    assert E[0] == pytest.approx(E0, rel=1e-13)
+    assert np.all(np.diff(E) <= 0) and len(E) < 60
+    rms = np.sqrt(E[-1] / sc.nobs)
+    assert 0.9 * 0.005 * np.sqrt(2) < rms < 1.1 * 0.005 * np.sqrt(2)
+    # the reported final cost is the oracle's cost of the returned state (gauge-invariant)
+    Xf, Rf, tf = O.normalize_gauge(X, R, t, sc.axis)
+    assert E[-1] == pytest.approx(O.cost(obs, Xf, K[:, 0, 0].copy(), K[:, :2, 2].copy(), Rf, tf, sc.f0), rel=1e-9)
+    adj.engine.close()
+
+
+def test_thousand_camera_sparse_run_properties(ba):
+    """C4's shape at 1/50 of its points (1000 cameras x 20k points, 10 % visibility, n = 8993):
+    the whole LM run on the sparse path (matrix-free pair kernel, two-level Cholesky, grid-wide
+    back substitution).  Monotone cost, noise-level RMS, and the reported final cost equals the
+    oracle's cost function on the returned state."""
+    sc = ba.scenes.make_scene(1000, 20_000, seed=5, visibility=0.1)
+    adj = ba.BundleAdjuster.from_observations(sc.obs_ptr, sc.obs_cam, sc.obs_xy, sc.X0, sc.K0, sc.R0, sc.t0,
+                                              f0=sc.f0, axis=sc.axis, gauge_on_device=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        X, K, R, t = adj.optimize(2.0, 1e-8, max_iter=100)
+    E = np.array([adj.records[0]["E_prev"]] + [r["E"] for r in adj.records])
+    assert np.all(np.diff(E) <= 0) and 3 < len(E) < 60
+    rms = np.sqrt(E[-1] / sc.nobs)
+    assert 0.85 * 0.005 * np.sqrt(2) < rms < 1.1 * 0.005 * np.sqrt(2)
+    obs = O.ObsList(sc.n_points, sc.n_cams, np.repeat(np.arange(sc.n_points), np.diff(sc.obs_ptr)),
+                    sc.obs_cam.astype(np.int64), sc.obs_xy, sc.obs_ptr)
+    Xf, Rf, tf = O.normalize_gauge(X, R, t, sc.axis)
+    assert E[-1] == pytest.approx(O.cost(obs, Xf, K[:, 0, 0].copy(), K[:, :2, 2].copy(), Rf, tf, sc.f0), rel=1e-9)
+    Xn, Rn, tn = O.normalize_gauge(sc.X0, sc.R0, sc.t0, sc.axis)
+    assert E[0] == pytest.approx(O.cost(obs, Xn, sc.K0[:, 0, 0].copy(), sc.K0[:, :2, 2].copy(), Rn, tn, sc.f0), rel=1e-11)
+    adj.engine.close()
 
 
 def test_shadow_module_intercepts_reference_import(ba):
