@@ -18,6 +18,10 @@ def __getattr__(name):
         from . import projection
 
         return getattr(projection, name)
+    if name in ("projective_depth_primary", "compute_projective_depth_primary_method"):
+        from . import projective_depth
+
+        return getattr(projective_depth, name)
     if name == "Engine":
         from . import engine
 

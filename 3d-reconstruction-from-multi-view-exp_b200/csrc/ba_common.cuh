@@ -268,6 +268,18 @@ int launch_camera_blocks(ba_engine* e, cudaStream_t s, bool conditional);
 int launch_k2b(ba_engine* e, bool conditional, double c_host, cudaStream_t s);
 int launch_k3(ba_engine* e, bool conditional, cudaStream_t s);
 int syrk_plan_engine(ba_engine* e);
+// Gram matrix P = Yt^T Yt of a k-major operand outside an engine (k3_schur_syrk.cu)
+struct GramWorkspace {
+  int n_pad = 0, num_sms = 0, n_items = 0, n_tiles = 0;
+  int64_t k_pad = 0;
+  SyrkItem* items = nullptr;
+  int* tile_first = nullptr;
+  int* tile_items = nullptr;
+  double* Spart = nullptr;
+};
+int gram_prepare(GramWorkspace* ws, int n_pad, int64_t k_pad, int num_sms, cudaStream_t s);
+int gram_launch(const GramWorkspace* ws, const double* Yt, double* P, cudaStream_t s);
+void gram_release(GramWorkspace* ws, cudaStream_t s);
 int syrk_plan_selftest(int n_cams, int64_t n_points, int tile, int num_sms, int* n_items, int* n_tiles,
                        double* makespan_rows, double* ideal_rows);
 int launch_assemble(ba_engine* e, bool conditional, double c_host, cudaStream_t s);

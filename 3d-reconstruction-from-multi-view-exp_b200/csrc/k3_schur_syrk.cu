@@ -541,6 +541,52 @@ int launch_k3(ba_engine* e, bool conditional, cudaStream_t s) {
   return launch_schur_sparse(e, ctl, s);
 }
 
+// ---- Gram matrix of an arbitrary k-major operand (used by the projective-depth iteration) --------
+// P = Yt^T Yt (lower triangle incl. the diagonal pairs) for Yt [k_pad][n_pad], with the 64-tile
+// kernel and the same planner as the Schur product.
+int gram_prepare(GramWorkspace* ws, int n_pad, int64_t k_pad, int num_sms, cudaStream_t s) {
+  *ws = GramWorkspace();
+  const SyrkPlan& plan = cached_plan(n_pad, 64, k_pad, num_sms);
+  ws->n_pad = n_pad;
+  ws->k_pad = k_pad;
+  ws->num_sms = num_sms;
+  ws->n_items = (int)plan.items.size();
+  const int nt1 = (n_pad + 63) / 64;
+  ws->n_tiles = nt1 * (nt1 + 1) / 2;
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws->items), plan.items.size() * sizeof(SyrkItem), s));
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws->tile_first), plan.tile_first.size() * sizeof(int), s));
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws->tile_items), plan.tile_items.size() * sizeof(int), s));
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws->Spart), plan.items.size() * (size_t)64 * 64 * sizeof(double), s));
+  BA_CUDA(cudaMemcpyAsync(ws->items, plan.items.data(), plan.items.size() * sizeof(SyrkItem), cudaMemcpyHostToDevice, s));
+  BA_CUDA(cudaMemcpyAsync(ws->tile_first, plan.tile_first.data(), plan.tile_first.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  BA_CUDA(cudaMemcpyAsync(ws->tile_items, plan.tile_items.data(), plan.tile_items.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  BA_CUDA(cudaStreamSynchronize(s));  // the plan's host vectors are cached, but keep the copies simple
+  return BA_OK;
+}
+
+int gram_launch(const GramWorkspace* ws, const double* Yt, double* P, cudaStream_t s) {
+  constexpr int TILE = 64, KC = 16;
+  const size_t smem = (size_t)2 * kStages * KC * (TILE + 4) * sizeof(double);
+  BA_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<TILE, 2, 2, KC, false>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  syrk_dmma_kernel<TILE, 2, 2, KC, false><<<ws->n_items, 128, smem, s>>>(
+      Yt, ws->n_pad, ws->n_pad, ws->k_pad / KC, ws->items, ws->Spart, nullptr, 0, SubSplit{0, 1, 0, 0, {}});
+  BA_LAUNCH_CHECK();
+  int slabs = 1;
+  while (slabs < TILE * TILE / 2 / 256 && ws->n_tiles * slabs < 4 * ws->num_sms) slabs *= 2;
+  syrk_reduce_kernel<TILE><<<dim3(ws->n_tiles, slabs), 256, 0, s>>>(ws->Spart, ws->tile_first, ws->tile_items, P,
+                                                                  ws->n_pad, ws->n_pad, nullptr);
+  BA_LAUNCH_CHECK();
+  return BA_OK;
+}
+
+void gram_release(GramWorkspace* ws, cudaStream_t s) {
+  void* ptrs[] = {ws->items, ws->tile_first, ws->tile_items, ws->Spart};
+  for (void* p : ptrs)
+    if (p) cudaFreeAsync(p, s);
+  *ws = GramWorkspace();
+}
+
 // Host-only check of the planner (no device needed): every tile's pieces must tile [0, n_chunks)
 // exactly once, in ascending order.
 int syrk_plan_selftest(int n_cams, int64_t n_points, int tile, int num_sms, int* n_items, int* n_tiles,

@@ -1,0 +1,523 @@
+// Projective-depth iteration, primary method -- the step BEFORE bundle adjustment in the reference's
+// perspective pipeline.
+//
+// Replaces reference lib/perspective_camera_calibration.py:61-144
+// (_compute_projective_depth_primary_method) together with _compute_reprojection_error (:44-58).
+// Per iteration the reference forms W = x * z with unit-length point vectors (:86-90), takes the
+// four leading left singular vectors U_ of the (3M x N) matrix (:92-96), solves for every point an
+// M x M symmetric eigenproblem (:98-125) whose leading eigenvector gives the new depths (:127-131),
+// and evaluates the reprojection error of the rank-4 approximation (:133-136).
+//
+// Here, with the two identities stated in oracle/depth_oracle.py (the point matrices are B B^T with
+// B of size M x 4; everything depends on U_ only through the projector U_ U_^T):
+//   depth_scale_kernel   warp per point: w = x z / |x z|  ->  Wn [N_pad][ld]  (k-major: row = point)
+//   Gram matrix          G = Wn^T Wn (3M x 3M) on the FP64 tensor cores -- the Schur-product SYRK
+//                        kernel of K3 (k3_schur_syrk.cu), work items planned on the host
+//   subspace_eig_kernel  one CTA: orthogonal iteration Q <- orth(G Q), warm-started from the previous
+//                        pass; U4 = an orthonormal basis of the dominant four-dimensional eigenspace
+//   jacobi_eig_kernel    fallback when that does not converge (near-degenerate 4th / 5th eigenvalue):
+//                        parallel cyclic Jacobi (round-robin pairs) on G, eigenvectors of the four
+//                        largest eigenvalues
+//   depth_update_kernel  warp per point: B (M x 4), 4 x 4 Gram, its leading eigenvector by Jacobi in
+//                        registers, xi = B v / |B v| with the sign rule of :127-128, z = xi / |x|; and
+//                        the point's share of the reprojection error (U4 U4^T w against x)
+//   depth_error_kernel   fixed-order sum of the partials -> E = f0 sqrt(mean)
+// The host reads one double (E) per iteration to apply the stopping rule of :138-142.
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "ba_common.cuh"
+
+namespace ba {
+
+// ---- Wn ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+depth_scale_kernel(int64_t N, int M, int ld, const double* __restrict__ x, const double* __restrict__ z,
+                   double* __restrict__ Wn) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = warp; j < N; j += nwarps) {
+    const double* xj = x + (size_t)j * M * 3;
+    const double* zj = z + (size_t)j * M;
+    double s = 0.0;
+    for (int a = lane; a < 3 * M; a += 32) {
+      const double w = xj[a] * zj[a / 3];
+      s += w * w;
+    }
+    s = warp_sum(s);
+    const double inv = 1.0 / sqrt(s);  // :90  W / ||W_j||
+    double* out = Wn + (size_t)j * ld;
+    for (int a = lane; a < ld; a += 32) out[a] = a < 3 * M ? (xj[a] * zj[a / 3]) * inv : 0.0;
+  }
+}
+
+// G (n x n, full symmetric, ld = n) from the lower triangle the SYRK reduce wrote into P (ld = n_pad)
+__global__ void gram_symmetrize_kernel(int n, int n_pad, const double* __restrict__ P, double* __restrict__ G) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n * n) return;
+  const int r = k / n, c = k - r * n;
+  G[k] = r >= c ? P[(size_t)r * n_pad + c] : P[(size_t)c * n_pad + r];
+}
+
+// ---- leading four-dimensional eigenspace of the Gram matrix: subspace iteration -----------------
+// Everything downstream depends on U4 only through the projector U4 U4^T, so any orthonormal basis
+// of the dominant invariant subspace will do.  One CTA iterates Q <- orth(G Q) (Cholesky-QR twice
+// per step) from the previous pass's basis (the depths change little between passes), until the
+// basis moves by less than 1e-13 in the Frobenius norm, plus two more steps; G is read through L1.
+// status[0] = 1 when it converged; otherwise the Jacobi kernel below takes over (near-degenerate
+// fourth and fifth eigenvalues).  Fixed order of operations: bit-reproducible.
+__global__ void __launch_bounds__(256)
+subspace_eig_kernel(int n, const double* __restrict__ G, double* __restrict__ U4, int warm, int max_steps,
+                    int* __restrict__ status) {
+  extern __shared__ double ssm[];
+  double* Q = ssm;           // [n][4]
+  double* Y = ssm + 4 * n;   // [n][4]
+  __shared__ double S[16], Rinv[16], Mq[16];
+  __shared__ double dist2[8];
+  __shared__ int s_stop;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+
+  // Y <- Y R^-1 with R^T R = Y^T Y  (one Cholesky-QR step; the caller runs it twice)
+  auto cholqr = [&]() {
+    for (int pr = warp; pr < 10; pr += nw) {  // the 10 entries k <= l of Y^T Y, one warp each
+      int k = 0, l = pr;
+      while (l >= 4 - k) { l -= 4 - k; ++k; }
+      l += k;
+      double acc = 0.0;
+      for (int a = lane; a < n; a += 32) acc += Y[4 * a + k] * Y[4 * a + l];
+      acc = warp_sum(acc);
+      if (lane == 0) { S[4 * k + l] = acc; S[4 * l + k] = acc; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double R[4][4] = {};
+      for (int c = 0; c < 4; ++c) {       // upper-triangular R, column by column
+        for (int r = 0; r <= c; ++r) {
+          double v = S[4 * r + c];
+          for (int m = 0; m < r; ++m) v -= R[m][r] * R[m][c];
+          R[r][c] = r == c ? sqrt(v) : v / R[r][r];
+        }
+      }
+      double I[4][4] = {};                // R^-1 (upper triangular) by back substitution
+      for (int c = 0; c < 4; ++c) {
+        I[c][c] = 1.0 / R[c][c];
+        for (int r = c - 1; r >= 0; --r) {
+          double v = 0.0;
+          for (int m = r + 1; m <= c; ++m) v -= R[r][m] * I[m][c];
+          I[r][c] = v / R[r][r];
+        }
+      }
+      for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) Rinv[4 * r + c] = I[r][c];
+    }
+    __syncthreads();
+    for (int a = tid; a < n; a += nt) {
+      const double y0 = Y[4 * a], y1 = Y[4 * a + 1], y2 = Y[4 * a + 2], y3 = Y[4 * a + 3];
+      Y[4 * a] = y0 * Rinv[0];
+      Y[4 * a + 1] = y0 * Rinv[1] + y1 * Rinv[5];
+      Y[4 * a + 2] = y0 * Rinv[2] + y1 * Rinv[6] + y2 * Rinv[10];
+      Y[4 * a + 3] = y0 * Rinv[3] + y1 * Rinv[7] + y2 * Rinv[11] + y3 * Rinv[15];
+    }
+    __syncthreads();
+  };
+
+  if (warm) {
+    for (int k = tid; k < 4 * n; k += nt) Y[k] = U4[k];
+  } else {
+    // cold start: four columns of G spread over the index range
+    for (int k = tid; k < 4 * n; k += nt) {
+      const int a = k >> 2, c = ((k & 3) * n) / 4 + (k & 3);
+      Y[k] = G[(size_t)a * n + (c < n ? c : n - 1)] + ((a == c) ? 1.0 : 0.0);
+    }
+  }
+  __syncthreads();
+  cholqr();
+  cholqr();
+  for (int k = tid; k < 4 * n; k += nt) Q[k] = Y[k];
+  __syncthreads();
+  int extra = -1;  // thread 0 only; >= 0: steps done after the basis stopped moving
+  int step = 0;
+  for (; step < max_steps; ++step) {
+    for (int w = tid; w < 4 * n; w += nt) {  // Y = G Q
+      const int a = w >> 2, k = w & 3;
+      const double* g = G + (size_t)a * n;
+      double acc0 = 0.0, acc1 = 0.0;
+      int b = 0;
+      for (; b + 1 < n; b += 2) {
+        acc0 = fma(g[b], Q[4 * b + k], acc0);
+        acc1 = fma(g[b + 1], Q[4 * (b + 1) + k], acc1);
+      }
+      if (b < n) acc0 = fma(g[b], Q[4 * b + k], acc0);
+      Y[w] = acc0 + acc1;
+    }
+    __syncthreads();
+    cholqr();
+    cholqr();
+    // how far did the basis move?  D = Y - Q (Q^T Y)
+    for (int pr = warp; pr < 16; pr += nw) {
+      const int k = pr >> 2, l = pr & 3;
+      double acc = 0.0;
+      for (int a = lane; a < n; a += 32) acc += Q[4 * a + k] * Y[4 * a + l];
+      acc = warp_sum(acc);
+      if (lane == 0) Mq[pr] = acc;
+    }
+    __syncthreads();
+    double d2 = 0.0;
+    for (int w = tid; w < 4 * n; w += nt) {
+      const int a = w >> 2, l = w & 3;
+      const double dd = Y[w] - (Q[4 * a] * Mq[l] + Q[4 * a + 1] * Mq[4 + l] + Q[4 * a + 2] * Mq[8 + l] +
+                                Q[4 * a + 3] * Mq[12 + l]);
+      d2 += dd * dd;
+    }
+    d2 = warp_sum(d2);
+    if (lane == 0) dist2[warp] = d2;
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < nw; ++w) tot += dist2[w];
+      if (extra < 0 && tot <= 1e-26) extra = 0;
+      else if (extra >= 0) ++extra;
+      s_stop = extra >= 2;
+    }
+    for (int k = tid; k < 4 * n; k += nt) Q[k] = Y[k];
+    __syncthreads();
+    if (s_stop) break;
+  }
+  for (int k = tid; k < 4 * n; k += nt) U4[k] = Q[k];
+  if (tid == 0) status[0] = step < max_steps ? 1 : 0;
+}
+
+// ---- symmetric eigenproblem of the Gram matrix ---------------------------------------------------
+// Parallel cyclic Jacobi in one CTA.  The n indices (padded to an even count with a dummy) are
+// paired round-robin, n/2 disjoint rotations per step, n - 1 steps per sweep: each step computes
+// the rotation angles, rotates the columns of G and V, then the rows of G.  Fixed order, fixed
+// stopping rule: bit-reproducible.  G and V live in global memory (L1/L2 resident: n <= 192).
+__global__ void __launch_bounds__(256)
+jacobi_eig_kernel(int n, double* __restrict__ G, double* __restrict__ V, double* __restrict__ U4,
+                  double* __restrict__ evals4, const int* __restrict__ status) {
+  if (status && status[0] == 1) return;  // the subspace iteration already delivered U4
+  extern __shared__ double jsm[];
+  const int ne = n + (n & 1), h = ne / 2;
+  double* cs = jsm;                                  // [h][2]
+  int* pl = reinterpret_cast<int*>(jsm + 2 * h);     // [ne] players
+  int* tmp = pl + ne;                                // [ne]
+  __shared__ double scratch[32];
+  __shared__ int s_done;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int k = tid; k < n * n; k += nt) V[k] = (k / n == k % n) ? 1.0 : 0.0;
+  for (int k = tid; k < ne; k += nt) pl[k] = k;
+  __syncthreads();
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int k = tid; k < n * n; k += nt) {
+      const double v = G[k];
+      if (k / n == k % n) dg += v * v; else off += v * v;
+    }
+    off = block_sum(off, scratch);
+    dg = block_sum(dg, scratch);
+    if (tid == 0) s_done = !(off > 1e-31 * dg);
+    __syncthreads();
+    if (s_done) break;
+    for (int step = 0; step < ne - 1; ++step) {
+      if (tid < h) {
+        int p = pl[tid], q = pl[ne - 1 - tid];
+        if (p > q) { const int t = p; p = q; q = t; }
+        double c = 1.0, s = 0.0;
+        if (q < n) {
+          const double apq = G[(size_t)p * n + q];
+          if (apq != 0.0) {
+            const double tau = (G[(size_t)q * n + q] - G[(size_t)p * n + p]) / (2.0 * apq);
+            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + t * t);
+            s = t * c;
+          }
+        }
+        cs[2 * tid] = c;
+        cs[2 * tid + 1] = s;
+      }
+      __syncthreads();
+      // columns p, q of G and V
+      for (int w = tid; w < h * n; w += nt) {
+        const int k = w / n, r = w - k * n;
+        int p = pl[k], q = pl[ne - 1 - k];
+        if (p > q) { const int t = p; p = q; q = t; }
+        if (q >= n) continue;
+        const double c = cs[2 * k], s = cs[2 * k + 1];
+        const double gp = G[(size_t)r * n + p], gq = G[(size_t)r * n + q];
+        G[(size_t)r * n + p] = c * gp - s * gq;
+        G[(size_t)r * n + q] = s * gp + c * gq;
+        const double vp = V[(size_t)r * n + p], vq = V[(size_t)r * n + q];
+        V[(size_t)r * n + p] = c * vp - s * vq;
+        V[(size_t)r * n + q] = s * vp + c * vq;
+      }
+      __syncthreads();
+      // rows p, q of G
+      for (int w = tid; w < h * n; w += nt) {
+        const int k = w / n, r = w - k * n;
+        int p = pl[k], q = pl[ne - 1 - k];
+        if (p > q) { const int t = p; p = q; q = t; }
+        if (q >= n) continue;
+        const double c = cs[2 * k], s = cs[2 * k + 1];
+        const double gp = G[(size_t)p * n + r], gq = G[(size_t)q * n + r];
+        G[(size_t)p * n + r] = c * gp - s * gq;
+        G[(size_t)q * n + r] = s * gp + c * gq;
+      }
+      __syncthreads();
+      // next round of the tournament: player 0 stays, the others move on by one seat
+      for (int k = tid; k < ne; k += nt) tmp[k] = k == 0 ? pl[0] : (k == 1 ? pl[ne - 1] : pl[k - 1]);
+      __syncthreads();
+      for (int k = tid; k < ne; k += nt) pl[k] = tmp[k];
+      __syncthreads();
+    }
+  }
+  // the four largest eigenvalues (selection in a fixed order) and their eigenvectors
+  __shared__ int top[4];
+  if (tid == 0) {
+    for (int k = 0; k < 4; ++k) {
+      int best = -1;
+      for (int a = 0; a < n; ++a) {
+        bool used = false;
+        for (int m = 0; m < k; ++m) used |= top[m] == a;
+        if (!used && (best < 0 || G[(size_t)a * n + a] > G[(size_t)best * n + best])) best = a;
+      }
+      top[k] = best;
+      evals4[k] = G[(size_t)best * n + best];
+    }
+  }
+  __syncthreads();
+  for (int w = tid; w < 4 * n; w += nt) {
+    const int a = w >> 2, k = w & 3;
+    U4[w] = V[(size_t)a * n + top[k]];
+  }
+}
+
+// ---- per point: new depths and the reprojection error ---------------------------------------------
+// Leading eigenvector of a symmetric 4 x 4 matrix by cyclic Jacobi in registers (every lane of the
+// warp runs it on identical inputs).
+__device__ __forceinline__ void top_eigvec4(double (&a)[4][4], double (&v)[4]) {
+  double e[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) e[r][c] = r == c ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 12; ++sweep) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 4; ++q) {
+        const double apq = a[p][q];
+        if (apq == 0.0) continue;
+        const double tau = (a[q][q] - a[p][p]) / (2.0 * apq);
+        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const double gp = a[r][p], gq = a[r][q];
+          a[r][p] = c * gp - s * gq;
+          a[r][q] = s * gp + c * gq;
+          const double vp = e[r][p], vq = e[r][q];
+          e[r][p] = c * vp - s * vq;
+          e[r][q] = s * vp + c * vq;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const double gp = a[p][r], gq = a[q][r];
+          a[p][r] = c * gp - s * gq;
+          a[q][r] = s * gp + c * gq;
+        }
+      }
+  }
+  int best = 0;
+#pragma unroll
+  for (int k = 1; k < 4; ++k)
+    if (a[k][k] > a[best][best]) best = k;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) v[r] = best == 0 ? e[r][0] : (best == 1 ? e[r][1] : (best == 2 ? e[r][2] : e[r][3]));
+}
+
+__global__ void __launch_bounds__(256)
+depth_update_kernel(int64_t N, int M, int ld, const double* __restrict__ x, const double* __restrict__ Wn,
+                    const double* __restrict__ U4, double* __restrict__ z, double* __restrict__ err_part) {
+  extern __shared__ double su[];  // U4 [3M][4]
+  __shared__ double scratch[32];
+  for (int k = threadIdx.x; k < 12 * M; k += blockDim.x) su[k] = U4[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double err = 0.0;
+  for (int64_t j = warp; j < N; j += nwarps) {
+    const double* xj = x + (size_t)j * M * 3;
+    // coefficients of the point in the leading subspace: c = U4^T w   (M S = U4 U4^T W, :133-134)
+    double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int a = lane; a < 3 * M; a += 32) {
+      const double w = Wn[(size_t)j * ld + a];
+      c0 += w * su[4 * a]; c1 += w * su[4 * a + 1]; c2 += w * su[4 * a + 2]; c3 += w * su[4 * a + 3];
+    }
+    c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); c3 = warp_sum(c3);
+    // 4 x 4 Gram of B (:98-113 in factored form) and the reprojection error of this pass (:44-58)
+    double g[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = lane; i < M; i += 32) {
+      const double x0 = xj[3 * i], x1 = xj[3 * i + 1], x2 = xj[3 * i + 2];
+      const double inv = 1.0 / sqrt(x0 * x0 + x1 * x1 + x2 * x2);
+      const double* u = su + 12 * i;  // rows 3i, 3i+1, 3i+2 of U4
+      double b[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) b[k] = (x0 * u[k] + x1 * u[4 + k] + x2 * u[8 + k]) * inv;
+      int idx = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int cc = r; cc < 4; ++cc) g[idx++] += b[r] * b[cc];
+      const double p0 = u[0] * c0 + u[1] * c1 + u[2] * c2 + u[3] * c3;
+      const double p1 = u[4] * c0 + u[5] * c1 + u[6] * c2 + u[7] * c3;
+      const double p2 = u[8] * c0 + u[9] * c1 + u[10] * c2 + u[11] * c3;
+      const double d0 = x0 - p0 / p2, d1 = x1 - p1 / p2, d2 = x2 - p2 / p2;
+      err += d0 * d0 + d1 * d1 + d2 * d2;
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) g[k] = warp_sum(g[k]);
+    double a[4][4], v[4];
+    {
+      int idx = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int cc = r; cc < 4; ++cc) { a[r][cc] = g[idx]; a[cc][r] = g[idx]; ++idx; }
+    }
+    top_eigvec4(a, v);
+    // xi = B v / |B v|, sign so that sum(xi) >= 0 (:127-128), z = xi / |x| (:131)
+    double nrm = 0.0, sum = 0.0;
+    for (int i = lane; i < M; i += 32) {
+      const double x0 = xj[3 * i], x1 = xj[3 * i + 1], x2 = xj[3 * i + 2];
+      const double inv = 1.0 / sqrt(x0 * x0 + x1 * x1 + x2 * x2);
+      const double* u = su + 12 * i;
+      double xi = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xi += (x0 * u[k] + x1 * u[4 + k] + x2 * u[8 + k]) * inv * v[k];
+      nrm += xi * xi;
+      sum += xi;
+    }
+    nrm = warp_sum(nrm);
+    sum = warp_sum(sum);
+    const double scale = (sum < 0.0 ? -1.0 : 1.0) / sqrt(nrm);
+    for (int i = lane; i < M; i += 32) {
+      const double x0 = xj[3 * i], x1 = xj[3 * i + 1], x2 = xj[3 * i + 2];
+      const double inv = 1.0 / sqrt(x0 * x0 + x1 * x1 + x2 * x2);
+      const double* u = su + 12 * i;
+      double xi = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xi += (x0 * u[k] + x1 * u[4 + k] + x2 * u[8 + k]) * inv * v[k];
+      z[(size_t)j * M + i] = xi * scale * inv;
+    }
+  }
+  const double tot = block_sum(err, scratch);
+  if (threadIdx.x == 0) err_part[blockIdx.x] = tot;
+}
+
+__global__ void depth_error_kernel(const double* __restrict__ part, int n, double count, double f0,
+                                   double* __restrict__ out) {
+  __shared__ double scratch[32];
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) acc += part[k];
+  const double tot = block_sum(acc, scratch);
+  if (threadIdx.x == 0) *out = f0 * sqrt(tot / count);  // :56
+}
+
+}  // namespace ba
+
+using namespace ba;
+
+extern "C" int ba_projective_depth_primary(int device, int64_t n_points, int32_t n_images, const double* x,
+                                           double f0, double tolerance, int max_iter, double* z,
+                                           double* errors, int* n_iter, int mem, void* stream) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: the projective-depth iteration has no CPU path");
+    return BA_ERR_NO_DEVICE;
+  }
+  if (!x || !z || !n_iter || n_points < 4 || n_images < 2 || n_images > 64 || max_iter < 1 || device < 0 ||
+      device >= ndev) {
+    set_error("projective depth: need >= 4 points, 2..64 images, max_iter >= 1 and valid pointers");
+    return BA_ERR_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  BA_CUDA(cudaSetDevice(device));
+  int num_sms = 148;
+  BA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+  const int64_t N = n_points;
+  const int M = n_images, n = 3 * M;
+  const int ld = (n + 7) / 8 * 8;
+  const int64_t k_pad = (N + 31) / 32 * 32;
+  const size_t d = sizeof(double);
+  double *dx = nullptr, *dz = nullptr, *Wn = nullptr, *P = nullptr, *G = nullptr, *V = nullptr, *U4 = nullptr,
+         *ev = nullptr, *part = nullptr, *dE = nullptr;
+  const int64_t blocks64 = (N + 7) / 8;
+  const int grid = balanced_blocks(blocks64, (int64_t)num_sms * 8);
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&Wn), (size_t)k_pad * ld * d, s));
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&P), (size_t)ld * ld * d, s));
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&G), (size_t)n * n * d, s));
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&V), (size_t)n * n * d, s));
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&U4), (size_t)4 * n * d, s));
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ev), 4 * d, s));
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&part), (size_t)grid * d, s));
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dE), d, s));
+  if (mem == BA_MEM_DEVICE) {
+    dx = const_cast<double*>(x);
+    dz = z;
+  } else {
+    BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dx), (size_t)N * M * 3 * d, s));
+    BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dz), (size_t)N * M * d, s));
+    BA_CUDA(cudaMemcpyAsync(dx, x, (size_t)N * M * 3 * d, cudaMemcpyHostToDevice, s));
+  }
+  BA_CUDA(cudaMemsetAsync(Wn, 0, (size_t)k_pad * ld * d, s));
+  BA_CUDA(cudaMemsetAsync(P, 0, (size_t)ld * ld * d, s));
+  {
+    std::vector<double> ones((size_t)N * M, 1.0);  // :80  z = 1
+    BA_CUDA(cudaMemcpyAsync(dz, ones.data(), ones.size() * d, cudaMemcpyHostToDevice, s));
+    BA_CUDA(cudaStreamSynchronize(s));
+  }
+  int* status = nullptr;
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&status), sizeof(int), s));
+  BA_CUDA(cudaMemsetAsync(status, 0, sizeof(int), s));
+  static const bool force_jacobi = std::getenv("BA_DEPTH_JACOBI") != nullptr;  // tests: the fallback path
+  GramWorkspace ws;
+  int st = gram_prepare(&ws, ld, k_pad, num_sms, s);
+  const size_t jac_smem = (size_t)(2 * ((n + 1) / 2)) * d + (size_t)2 * (n + 1) * sizeof(int) + 16;
+  int it = 0;
+  double E = 0.0;
+  while (st == BA_OK) {
+    depth_scale_kernel<<<grid, 256, 0, s>>>(N, M, ld, dx, dz, Wn);
+    st = gram_launch(&ws, Wn, P, s);
+    if (st != BA_OK) break;
+    gram_symmetrize_kernel<<<(n * n + 255) / 256, 256, 0, s>>>(n, ld, P, G);
+    if (!force_jacobi)
+      subspace_eig_kernel<<<1, 256, (size_t)8 * n * d, s>>>(n, G, U4, it > 0 ? 1 : 0, 2000, status);
+    jacobi_eig_kernel<<<1, 256, jac_smem, s>>>(n, G, V, U4, ev, force_jacobi ? nullptr : status);
+    depth_update_kernel<<<grid, 256, (size_t)12 * M * d, s>>>(N, M, ld, dx, Wn, U4, dz, part);
+    depth_error_kernel<<<1, 256, 0, s>>>(part, grid, (double)N * (double)M, f0, dE);
+    g_launch_count += 6;
+    if (cudaMemcpyAsync(&E, dE, d, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+      set_error("projective depth: %s", cudaGetErrorString(cudaGetLastError()));
+      st = BA_ERR_CUDA;
+      break;
+    }
+    if (errors) errors[it] = E;
+    ++it;
+    if (E < tolerance || it >= max_iter) break;  // :138-142
+  }
+  *n_iter = it;
+  if (st == BA_OK && mem != BA_MEM_DEVICE) {
+    if (cudaMemcpyAsync(z, dz, (size_t)N * M * d, cudaMemcpyDeviceToHost, s) != cudaSuccess) st = BA_ERR_CUDA;
+  }
+  gram_release(&ws, s);
+  void* frees[] = {Wn, P, G, V, U4, ev, part, dE, status, mem == BA_MEM_DEVICE ? nullptr : dx,
+                   mem == BA_MEM_DEVICE ? nullptr : dz};
+  for (void* p : frees)
+    if (p) cudaFreeAsync(p, s);
+  cudaStreamSynchronize(s);
+  return st;
+}

@@ -245,6 +245,17 @@ int ba_syrk_plan_info(int n_cams, int64_t n_points, int tile, int num_sms, int* 
 int ba_project_points(int device, int64_t n_points, int32_t n_cams, const double* X, const double* K,
                       const double* R, const double* t, double* out, int mem, void* stream);
 
+/* ---- before the path: projective-depth iteration, primary method --------------------------- */
+/* _compute_projective_depth_primary_method (reference lib/perspective_camera_calibration.py:61-144,
+ * with _compute_reprojection_error :44-58): x[n_points][n_images][3] are the rows (x/f0, y/f0, 1) of
+ * _create_data_matrix (:35-41); z[n_points][n_images] receives the projective depths; errors (may be
+ * NULL, else >= max_iter doubles) the reprojection error of every iteration (what the reference
+ * prints, :141); *n_iter the number of iterations run (stops when E < tolerance or at max_iter,
+ * :138-142).  2 <= n_images <= 64.  No engine needed; BA_MEM_HOST copies in and out. */
+int ba_projective_depth_primary(int device, int64_t n_points, int32_t n_images, const double* x, double f0,
+                                double tolerance, int max_iter, double* z, double* errors, int* n_iter,
+                                int mem, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
