@@ -303,6 +303,13 @@ __device__ __forceinline__ void top_eigvec4(double (&a)[4][4], double (&v)[4]) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) e[r][c] = r == c ? 1.0 : 0.0;
   for (int sweep = 0; sweep < 12; ++sweep) {
+    // converged?  (all lanes hold the same matrix: the branch is uniform.)  Cyclic Jacobi converges
+    // quadratically; a 4 x 4 matrix needs 4-5 sweeps, and each rotation costs two divisions and two
+    // square roots in FP64 -- the fixed 12 sweeps were 84 % of the whole pass in the launch list.
+    const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[0][3] * a[0][3] + a[1][2] * a[1][2] +
+                       a[1][3] * a[1][3] + a[2][3] * a[2][3];
+    const double dg = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2] + a[3][3] * a[3][3];
+    if (!(off > 1e-33 * dg)) break;
 #pragma unroll
     for (int p = 0; p < 3; ++p)
 #pragma unroll
