@@ -76,3 +76,64 @@ def projective_depth_primary(x: np.ndarray, f0: float, tolerance: float, max_ite
         if E < tolerance or len(errors) >= max_iter:
             break
     return z, errors
+
+
+# ---- dual method (reference :147-235) ---------------------------------------------------------------
+def dual_iteration(x: np.ndarray, z: np.ndarray, f0: float):
+    """One pass of the dual method (:163-222): returns (new z, E of this pass).
+
+    The reference normalises W per IMAGE (:171-176: every image's 3 x N block divided by its squared
+    Frobenius norm), takes the four leading RIGHT singular vectors V_ (N x 4, :178-181) and solves,
+    per image i, the N x N eigenproblem of B_i[j][l] = (v_j . v_l)(x_ij . x_il) / (|x_ij| |x_il|)
+    (:183-204).  B_i = C_i C_i^T with the N x 12 matrix C_i[j][(a, b)] = v_j[a] x_ij[b] / |x_ij|, so
+    its leading eigenvector is C_i w / |C_i w| with w from the 12 x 12 matrix C_i^T C_i.
+
+    Sign: the reference takes LAPACK's eigenvector as is and then flips ROWS of the (N, M) array whose
+    sum is negative (:212-215) -- a rule carried over from the primary method that does not fix the
+    per-image sign.  The sign of column i of z is therefore LAPACK's choice; it cancels in every later
+    pass (V_ does not depend on it) and in the Euclidean upgrade.  This restatement fixes the
+    per-image sign by making each column's sum non-negative BEFORE applying the reference's row rule;
+    callers compare with the reference up to a sign per image.
+    """
+    N, M = z.shape
+    W = x * z[..., None]                                        # (N, M, 3)
+    per_image = (W * W).sum(axis=(0, 2))                        # squared Frobenius norm of image i's block
+    Wn = (W / per_image[None, :, None]).reshape(N, 3 * M)       # (:171-176)
+    # leading right singular vectors of the (3M x N) matrix = leading eigenvectors of Wn Wn^T (N x N)
+    # = Wn U4 Sigma^-1 with U4 from the small Gram matrix Wn^T Wn (3M x 3M)
+    G = Wn.T @ Wn
+    vals, vecs = np.linalg.eigh(G)
+    order = np.argsort(vals)[::-1][:4]
+    U4, sig = vecs[:, order], np.sqrt(vals[order])
+    V4 = (Wn @ U4) / sig                                        # (N, 4), orthonormal columns
+    xn = np.sqrt((x * x).sum(axis=2))                           # (N, M)
+    xh = x / xn[..., None]
+    xi = np.empty((N, M))
+    for i in range(M):
+        Ci = (V4[:, :, None] * xh[:, i, None, :]).reshape(N, 12)
+        wv, wvec = np.linalg.eigh(Ci.T @ Ci)
+        e = Ci @ wvec[:, np.argmax(wv)]
+        e /= np.sqrt((e * e).sum())
+        xi[:, i] = e if e.sum() >= 0 else -e
+    xi[xi.sum(axis=1) < 0] *= -1.0                              # (:212-215), verbatim
+    z_new = xi / xn
+    # E (:219-221): M = U[:, :4], S = diag(Sigma[:4]) V_^T  ->  M S = U4 U4^T Wn^T
+    c = Wn @ U4
+    Uc = U4.reshape(M, 3, 4)
+    PX = np.einsum("ick,jk->jic", Uc, c)
+    PX = PX / PX[..., 2:3]
+    d = x - PX
+    return z_new, float(f0 * np.sqrt((d * d).sum(axis=2).mean()))
+
+
+def projective_depth_dual(x: np.ndarray, f0: float, tolerance: float, max_iter: int = 50):
+    """(:147-235) up to a sign per image (see dual_iteration)."""
+    x = np.asarray(x, dtype=np.float64)
+    z = np.ones(x.shape[:2])
+    errors = []
+    while True:
+        z, E = dual_iteration(x, z, f0)
+        errors.append(E)
+        if E < tolerance or len(errors) >= max_iter:
+            break
+    return z, errors
