@@ -2,8 +2,13 @@
 
 Every rank owns a contiguous shard of the points with all their observations and evaluates
 residuals, Jacobians, point blocks and its share of the Schur products locally.  Per inner
-solve there are exactly two exchanges, both ``all_reduce(SUM)`` over
-``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the CPU tests):
+solve there are exactly two exchanges.
+
+This module is the ``exchange="collective"`` form: both are ``all_reduce(SUM)`` over
+``torch.distributed`` (NCCL over NVLink on a GPU box, gloo in the CPU tests).  The default on
+NCCL groups is ``exchange="peer"``: the sums are kernels of the library itself over NVLink peer
+memory (``csrc/comm_peer.cu``), the loop is the single-engine CUDA-graph loop (``ba_lm_run``), and
+nothing of this module but ``shard_bounds`` is used.  The two exchanges:
 
   1. the partial reduced system  [sum_j Y_j Y_j^T | rhs row | U_i | dF_i]  (one flat buffer),
   2. the trial cost (one double).
