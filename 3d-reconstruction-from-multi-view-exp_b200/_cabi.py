@@ -54,6 +54,7 @@ SIGNATURES = {
     "ba_create": (C.c_int, [C.POINTER(Problem), C.POINTER(_P)]),
     "ba_destroy": (C.c_int, [_P]),
     "ba_set_observations": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
+    "ba_set_observations_dense": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, _P]),
     "ba_set_state": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "ba_get_state": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P]),
     "ba_set_state_global": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, _P]),

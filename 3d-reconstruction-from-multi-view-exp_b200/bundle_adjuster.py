@@ -30,9 +30,12 @@ class ObservationList:
 
     obs_ptr: np.ndarray  # (N+1,) int64
     obs_cam: np.ndarray | None  # (nobs,) int32; None when dense
-    obs_xy: np.ndarray  # (nobs, 2) float64
+    obs_xy: np.ndarray | None  # (nobs, 2) float64; None when `dense_x` carries the block
     n_cams: int
     dense: bool
+    # the caller's dense ``x (N, M, 2)`` itself when it is one point-major or camera-major block of
+    # float64: uploaded as it lies in memory and re-ordered on the device (ba_set_observations_dense)
+    dense_x: np.ndarray | None = None
 
     @property
     def n_points(self) -> int:
@@ -40,6 +43,8 @@ class ObservationList:
 
     @property
     def n_obs(self) -> int:
+        if self.obs_xy is None:
+            return int(self.dense_x.shape[0] * self.dense_x.shape[1])
         return int(self.obs_xy.shape[0])
 
     @staticmethod
@@ -47,8 +52,12 @@ class ObservationList:
         """Reference layout: ``x (N, M, 2)`` (any strides) and an optional bool mask (N, M)."""
         N, M = x.shape[:2]
         if visibility_index is None or bool(np.all(visibility_index)):
-            xy = np.ascontiguousarray(x, dtype=np.float64).reshape(N * M, 2)
             ptr = np.arange(N + 1, dtype=np.int64) * M
+            if isinstance(x, np.ndarray) and x.dtype == np.float64 and x.ndim == 3 and x.shape[2] == 2 \
+                    and x.strides[2] == 8 and (x.strides[0], x.strides[1]) in ((16 * M, 16), (16, 16 * N)):
+                # what both reference scripts pass: np.stack(x_list).transpose(1, 0, 2)
+                return ObservationList(ptr, None, None, M, True, dense_x=x)
+            xy = np.ascontiguousarray(x, dtype=np.float64).reshape(N * M, 2)
             return ObservationList(ptr, None, xy, M, True)
         vis = np.asarray(visibility_index, dtype=bool)
         pt, cam = np.nonzero(vis)
@@ -100,7 +109,10 @@ class BundleAdjuster:
         if device is None:
             device = _default_device()
         self._engine = Engine(self._n_points, self._n_images, obs.n_obs, self._f0, axis, obs.dense, device)
-        self._engine.set_observations(obs.obs_ptr, obs.obs_cam, obs.obs_xy)
+        if obs.dense_x is not None:
+            self._engine.set_observations_dense(obs.dense_x)
+        else:
+            self._engine.set_observations(obs.obs_ptr, obs.obs_cam, obs.obs_xy)
         if self._gauge_on_device:
             self._engine.set_state_global(init_X, init_R, init_t, self._f, self._u)
         else:

@@ -118,6 +118,32 @@ __global__ void cam_ptr_kernel(int M, int64_t n, const int32_t* __restrict__ key
   cam_ptr[i] = lo;
 }
 
+// obs_ptr of a dense scene: point j owns observations [j M, (j + 1) M)
+__global__ void dense_ptr_kernel(int64_t N, int M, int64_t* __restrict__ obs_ptr) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j <= N; j += stride) obs_ptr[j] = j * M;
+}
+
+// Camera-major image points src[M][N] (one double2 each) -> point-major dst[N][M]: 32 x 32 tiles
+// through shared memory, both sides coalesced.  grid = (ceil(N/32), ceil(M/32)), block = (32, 8).
+__global__ void transpose_xy_kernel(int64_t N, int M, const double2* __restrict__ src,
+                                    double2* __restrict__ dst) {
+  __shared__ double2 tile[32][33];
+  const int64_t j0 = (int64_t)blockIdx.x * 32;
+  const int i0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = i0 + r;
+    const int64_t j = j0 + threadIdx.x;
+    if (i < M && j < N) tile[r][threadIdx.x] = src[(int64_t)i * N + j];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int64_t j = j0 + r;
+    const int i = i0 + threadIdx.x;
+    if (i < M && j < N) dst[j * M + i] = tile[threadIdx.x][r];
+  }
+}
+
 // Stable (hence deterministic) radix sort of observation ids by camera: cm_perm, cam_ptr.
 int build_camera_major_index(ba_engine* e, cudaStream_t s) {
   const int64_t n = e->nobs;
@@ -440,6 +466,38 @@ int ba_set_observations(ba_engine* e, const int64_t* obs_ptr, const int32_t* obs
     BA_TRY(build_camera_major_index(e, s));
     BA_TRY(build_pair_index(e, s));
   }
+  BA_CUDA(cudaStreamSynchronize(s));
+  e->have_obs = true;
+  return BA_OK;
+}
+
+int ba_set_observations_dense(ba_engine* e, const double* x, int64_t stride_pt, int64_t stride_cam,
+                              int mem, void* stream) {
+  if (!e || !x) { set_error("null argument"); return BA_ERR_INVALID; }
+  if (!e->dense) { set_error("ba_set_observations_dense needs a dense problem"); return BA_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  BA_CUDA(cudaSetDevice(e->device));
+  const int64_t N = e->N;
+  const int M = e->M;
+  const size_t bytes = (size_t)e->nobs * 2 * sizeof(double);
+  if (stride_pt == 2 * (int64_t)M && stride_cam == 2) {
+    BA_TRY(copy_in(e->obs_xy, x, bytes, mem, s));  // already point-major
+  } else if (stride_pt == 2 && stride_cam == 2 * N) {
+    // camera-major block (np.stack(x_list).transpose(1, 0, 2)): copy it as it lies in memory into the
+    // camera-side Jacobian buffer (20 doubles per observation, not in use before the first
+    // linearisation) and re-order on the device
+    BA_TRY(copy_in(e->JC, x, bytes, mem, s));
+    const dim3 grid((unsigned)((N + 31) / 32), (unsigned)((M + 31) / 32));
+    transpose_xy_kernel<<<grid, dim3(32, 8), 0, s>>>(N, M, reinterpret_cast<const double2*>(e->JC),
+                                                     reinterpret_cast<double2*>(e->obs_xy));
+    BA_LAUNCH_CHECK();
+  } else {
+    set_error("dense observations must be one point-major or camera-major block (strides %lld, %lld)",
+              (long long)stride_pt, (long long)stride_cam);
+    return BA_ERR_INVALID;
+  }
+  dense_ptr_kernel<<<e->num_sms, 256, 0, s>>>(N, M, e->obs_ptr);
+  BA_LAUNCH_CHECK();
   BA_CUDA(cudaStreamSynchronize(s));
   e->have_obs = true;
   return BA_OK;

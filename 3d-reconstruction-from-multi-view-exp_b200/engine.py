@@ -92,6 +92,17 @@ class Engine:
             raise ValueError("observation arrays must all be host arrays or all be device tensors")
         _cabi.check(self._lib.ba_set_observations(self._h, p_ptr, p_cam, p_xy, mems.pop(), self.stream))
 
+    def set_observations_dense(self, x):
+        """Dense ``x (N, M, 2)`` float64 exactly as the reference constructor receives it (one
+        point-major or camera-major block, host array or CUDA tensor): no host-side copy."""
+        if hasattr(x, "data_ptr") and getattr(x, "is_cuda", False):
+            ptr, mem, strides = x.data_ptr(), _cabi.BA_MEM_DEVICE, tuple(x.stride())
+        else:
+            ptr, mem, strides = x.ctypes.data, _cabi.BA_MEM_HOST, tuple(s // 8 for s in x.strides)
+        if tuple(x.shape) != (self.n_points, self.n_cams, 2) or strides[2] != 1:
+            raise ValueError("x must be (n_points, n_cams, 2) with unit stride on the last axis")
+        _cabi.check(self._lib.ba_set_observations_dense(self._h, ptr, strides[0], strides[1], mem, self.stream))
+
     def set_state(self, X=None, R=None, t=None, f=None, u=None):
         ptrs, mems, keep = [], set(), []
         for a in (X, R, t, f, u):

@@ -2,8 +2,9 @@
 
 Mirrors reference ``lib/bundle_adjustment.py``: the saved camera-0 frame and baseline length
 (:23-33), ``_transform_to_normalize_coodinates`` (:208-240) and
-``_inverse_transform_to_global_coordinates`` (:242-258).  These stay on the host side of the
-C ABI (SURVEY.md section 8f ranks moving them to the device as the next step).
+``_inverse_transform_to_global_coordinates`` (:242-258).  This is the host form, used by the
+reference-signature constructor; ``gauge_on_device=True`` runs the same transforms as CUDA
+kernels behind ``ba_set_state_global`` / ``ba_get_state_global`` (``csrc/k6_gauge.cu``).
 """
 from __future__ import annotations
 

@@ -125,11 +125,23 @@ def make_scene(
     axis: str = "x-up_z-forward",
     chunk: int = 20000,
     point_stream: int = 0,
+    chunk_seeded: bool = False,
+    point_range: tuple[int, int] | None = None,
 ) -> Scene:
     """`seed` fixes the cameras (ground truth and initial perturbation); the points, their
     visibility and the image noise come from a second stream keyed by (`seed`,
     `point_stream`), so that the ranks of a sharded run share the cameras and draw disjoint
-    point shards (`point_stream = rank`)."""
+    point shards (`point_stream = rank`).
+
+    `chunk_seeded=True` keys that second stream per chunk of `chunk` points instead, so that any
+    contiguous `point_range=(lo, hi)` of the scene can be generated on its own and is identical
+    to rows lo:hi of the whole scene: the ranks of a strong-scaled run each build their shard of
+    the *same* global scene without anybody building all of it."""
+    if chunk_seeded:
+        return _make_scene_chunk_seeded(n_cams, n_points, seed, visibility, noise, outlier_frac, perturb,
+                                        f_scale, min_views, axis, chunk, point_stream, point_range)
+    if point_range is not None:
+        raise ValueError("point_range needs chunk_seeded=True")
     rs_cam = np.random.RandomState(seed)
     f0 = 1.0
     pos = hemisphere_positions(rs_cam, n_cams, 5.0)
@@ -186,10 +198,70 @@ def make_scene(
                  X0, K0, R0, t0, X_gt, K_gt, R_gt, t_gt)
 
 
-# The named benchmark configurations of BASELINE.json (`configs[1..4]`).
+def _cameras(seed: int, n_cams: int, perturb: float, f_scale: float, f0: float):
+    """Ground-truth cameras and their perturbed initial values (the `seed` stream of make_scene)."""
+    rs_cam = np.random.RandomState(seed)
+    pos = hemisphere_positions(rs_cam, n_cams, 5.0)
+    targets = rs_cam.normal(0, 0.5, (n_cams, 3))
+    R_gt = look_at(pos, targets)
+    t_gt = pos
+    t0 = t_gt + perturb * rs_cam.standard_normal(t_gt.shape)
+    R0 = rodrigues_batch(perturb * rs_cam.standard_normal((n_cams, 3))) @ R_gt
+    K_gt = np.zeros((n_cams, 3, 3))
+    K_gt[:, 0, 0] = K_gt[:, 1, 1] = 1.0
+    K_gt[:, 2, 2] = f0
+    K0 = K_gt.copy()
+    K0[:, 0, 0] *= f_scale
+    K0[:, 1, 1] *= f_scale
+    return R_gt, t_gt, K_gt, R0, t0, K0
+
+
+def _make_scene_chunk_seeded(n_cams, n_points, seed, visibility, noise, outlier_frac, perturb, f_scale,
+                             min_views, axis, chunk, point_stream, point_range) -> Scene:
+    f0 = 1.0
+    R_gt, t_gt, K_gt, R0, t0, K0 = _cameras(seed, n_cams, perturb, f_scale, f0)
+    f_gt, u_gt = np.ones(n_cams), np.zeros((n_cams, 2))
+    lo_pt, hi_pt = (0, n_points) if point_range is None else (int(point_range[0]), int(point_range[1]))
+    if not (0 <= lo_pt <= hi_pt <= n_points):
+        raise ValueError("point_range out of bounds")
+    dense = visibility >= 1.0
+    Xg, X0s, cnts, cams, xys = [], [], [], [], []
+    for ci in range(lo_pt // chunk, (max(hi_pt, lo_pt + 1) - 1) // chunk + 1):
+        c0, c1 = ci * chunk, min(n_points, (ci + 1) * chunk)
+        rs = np.random.RandomState([seed % (2**31 - 1), point_stream, ci, 0x5CE9E])
+        X_c = rs.uniform(-1, 1, (c1 - c0, 3))
+        if dense:
+            vis = np.ones((c1 - c0, n_cams), dtype=bool)
+        else:
+            vis = rs.random_sample((c1 - c0, n_cams)) < visibility
+            for j in np.nonzero(vis.sum(axis=1) < min_views)[0]:  # see make_scene
+                free = np.nonzero(~vis[j])[0]
+                vis[j, rs.choice(free, size=min_views - int(vis[j].sum()), replace=False)] = True
+        pt, cam = np.nonzero(vis)
+        xy = project_obs(X_c, f_gt, u_gt, R_gt, t_gt, f0, pt, cam)
+        xy += noise * rs.standard_normal(xy.shape)
+        if outlier_frac > 0:
+            bad = rs.random_sample(xy.shape[0]) < outlier_frac
+            xy[bad] = rs.uniform(-0.5, 0.5, (int(bad.sum()), 2))
+        X0_c = X_c + perturb * rs.standard_normal(X_c.shape)
+        # rows of this chunk inside the requested range
+        a, b = max(lo_pt, c0) - c0, min(hi_pt, c1) - c0
+        cnt = vis.sum(axis=1)
+        ptr_c = np.concatenate(([0], np.cumsum(cnt)))
+        Xg.append(X_c[a:b]); X0s.append(X0_c[a:b]); cnts.append(cnt[a:b])
+        cams.append(cam[ptr_c[a]:ptr_c[b]].astype(np.int32)); xys.append(xy[ptr_c[a]:ptr_c[b]])
+    counts = np.concatenate(cnts) if cnts else np.zeros(0, dtype=np.int64)
+    obs_ptr = np.concatenate(([0], np.cumsum(counts))).astype(np.int64)
+    return Scene(hi_pt - lo_pt, n_cams, f0, axis, obs_ptr, np.concatenate(cams),
+                 np.ascontiguousarray(np.concatenate(xys)), dense, np.concatenate(X0s), K0, R0, t0,
+                 np.concatenate(Xg), K_gt, R_gt, t_gt)
+
+
+# The named benchmark configurations of BASELINE.json (`configs[1..4]`).  c3-c5 are chunk-seeded so
+# that the ranks of a strong-scaled run can each generate their shard of the same global scene.
 CONFIGS = {
     "c2": dict(n_cams=50, n_points=10_000, visibility=1.0, seed=2),
-    "c3": dict(n_cams=200, n_points=100_000, visibility=1.0, seed=3),
-    "c4": dict(n_cams=1000, n_points=1_000_000, visibility=0.1, seed=4),
-    "c5": dict(n_cams=1000, n_points=1_000_000, visibility=0.1, outlier_frac=0.01, seed=5),
+    "c3": dict(n_cams=200, n_points=100_000, visibility=1.0, seed=3, chunk_seeded=True),
+    "c4": dict(n_cams=1000, n_points=1_000_000, visibility=0.1, seed=4, chunk_seeded=True),
+    "c5": dict(n_cams=1000, n_points=1_000_000, visibility=0.1, outlier_frac=0.01, seed=5, chunk_seeded=True),
 }

@@ -17,10 +17,13 @@
  *     failure on the calling thread;
  *   - state is held in the *normalised gauge frame* of the reference (camera 0 = identity at
  *     the origin, baseline component = +-1; lib/bundle_adjustment.py:208-240).  The O(N)
- *     normalise / denormalise steps stay on the host side of the boundary.
+ *     normalise / denormalise steps run either on the host side of the boundary (ba_set_state /
+ *     ba_get_state take and return the normalised frame) or on the device
+ *     (ba_set_state_global / ba_get_state_global take and return the caller's frame).
  *   - one engine per process and GPU.  Points may be sharded over several engines (one per
- *     rank); the camera block is replicated and the host all-reduces two device buffers per
- *     inner solve (ba_reduce_buffer / ba_cost_buffer) -- see the phase functions below.
+ *     rank); the camera block is replicated and two sums per inner solve run over the ranks:
+ *     by the library's own kernels over NVLink peer memory (ba_comm_*), or by the host
+ *     all-reducing two device buffers (ba_reduce_buffer / ba_cost_buffer) between the phases.
  */
 #ifndef BA_B200_H
 #define BA_B200_H
@@ -106,6 +109,15 @@ int ba_destroy(ba_engine* e);
  * NULL when problem.dense), obs_xy[n_obs][2].  Builds the camera-major index on the device. */
 int ba_set_observations(ba_engine* e, const int64_t* obs_ptr, const int32_t* obs_cam,
                         const double* obs_xy, int mem, void* stream);
+/* Dense observations exactly as the reference constructor receives them (`x`, :36-37): element
+ * (point j, camera i, c) lies at x[j * stride_pt + i * stride_cam + c] (strides in doubles).  Two
+ * layouts are taken: one point-major block (stride_pt = 2 n_cams, stride_cam = 2) and one
+ * camera-major block (stride_pt = 2, stride_cam = 2 n_points) -- what both reference scripts pass,
+ * np.stack(x_list).transpose(1, 0, 2) (euclidiean_reconstruction.py:54).  The block is copied as it
+ * lies in memory and re-ordered to point-major on the device, so the host never makes the
+ * contiguous copy.  Any other stride pattern returns BA_ERR_INVALID (copy on the host first). */
+int ba_set_observations_dense(ba_engine* e, const double* x, int64_t stride_pt, int64_t stride_cam,
+                              int mem, void* stream);
 /* State in the normalised frame: X[n_points][3], R[n_cams][3][3], t[n_cams][3], f[n_cams],
  * u[n_cams][2]  (:40-48).  Any pointer may be NULL to leave that part untouched. */
 int ba_set_state(ba_engine* e, const double* X, const double* R, const double* t,

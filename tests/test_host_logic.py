@@ -72,7 +72,14 @@ def test_observation_list_from_dense():
     assert not xt.flags.c_contiguous
     od = adjuster.ObservationList.from_dense(xt, None)
     assert od.dense and od.obs_cam is None and od.n_obs == x.shape[0] * x.shape[1]
-    np.testing.assert_array_equal(od.obs_xy.reshape(x.shape), x)
+    # a camera-major float64 block is handed over as it lies in memory (re-ordered on the device)
+    assert od.obs_xy is None and od.dense_x is xt
+    # anything else (another dtype, odd strides) is made contiguous on the host
+    oc = adjuster.ObservationList.from_dense(xt.astype(np.float32), None)
+    assert oc.dense_x is None
+    np.testing.assert_array_equal(oc.obs_xy.reshape(x.shape), x.astype(np.float32).astype(np.float64))
+    odd = np.zeros((x.shape[0], x.shape[1], 4))[:, :, :2]
+    assert adjuster.ObservationList.from_dense(odd, None).dense_x is None
     # an all-true mask is the dense case
     assert adjuster.ObservationList.from_dense(x, np.ones(x.shape[:2], bool)).dense
 
