@@ -16,7 +16,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libba_b200.so")
 
 (BA_OK, BA_ERR_INVALID, BA_ERR_CUDA, BA_ERR_SINGULAR, BA_ERR_STATE, BA_ERR_NO_DEVICE, BA_ERR_STALL,
- BA_ERR_COMM) = range(8)
+ BA_ERR_COMM, BA_ERR_BARRIER) = range(9)
 BA_COMM_HANDLE_BYTES = 88
 BA_MEM_HOST, BA_MEM_DEVICE = 0, 1
 BA_AXIS_X_RIGHT, BA_AXIS_X_UP = 0, 1

@@ -148,7 +148,7 @@ struct ba_engine {
   double* dxi = nullptr;    // [M][9]
   double* cost_part = nullptr;
   int cost_blocks = 0;
-  double* cost_buf = nullptr;  // [2]
+  double* cost_buf = nullptr;  // [4]: cost of the current / initial state, trial cost, "singular block" flag of the trial solve (summed over ranks with the cost), pad
 
   ba_lm_state* ctl = nullptr;       // device
   ba_iter_record* rec = nullptr;    // device [kMaxRecords]

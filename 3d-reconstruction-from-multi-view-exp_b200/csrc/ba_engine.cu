@@ -323,7 +323,7 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
   A(dev_alloc(&e->Winv, (size_t)((e->n_full + kCholNB - 1) / kCholNB) * kCholNB * kCholNB));
   A(dev_alloc(&e->dxi, (size_t)e->n_full));
   A(dev_alloc(&e->cost_part, (size_t)e->num_sms * 16 + 1024));
-  A(dev_alloc(&e->cost_buf, (size_t)2));
+  A(dev_alloc(&e->cost_buf, (size_t)4));
   A(dev_alloc(&e->ctl, (size_t)1));
   A(dev_alloc(&e->rec, (size_t)kMaxRecords));
 #undef A
@@ -339,7 +339,7 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
     cudaMemset(e->red, 0, (size_t)e->red_len * sizeof(double));
     if (e->Yt) cudaMemset(e->Yt, 0, (size_t)e->k_pad * e->n_pad * sizeof(double));
     cudaMemset(e->ctl, 0, sizeof(ba_lm_state));
-    cudaMemset(e->cost_buf, 0, 2 * sizeof(double));
+    cudaMemset(e->cost_buf, 0, 4 * sizeof(double));
     cudaMemset(e->dxi, 0, (size_t)e->n_full * sizeof(double));
     if (cudaDeviceSynchronize() != cudaSuccess) {
       set_error("device initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -401,6 +401,11 @@ static int status_from_ctl(const ba_lm_state& st) {
   if (st.status == BA_ERR_COMM) {
     set_error("a peer rank did not answer within the spin limit of the NVLink exchange");
     return BA_ERR_COMM;
+  }
+  if (st.status == BA_ERR_BARRIER) {
+    set_error("grid barrier of the back substitution timed out: its blocks were not co-resident "
+              "(is another kernel holding the GPU?)");
+    return BA_ERR_BARRIER;
   }
   if (st.status == BA_ERR_STALL) {
     set_error("inner LM loop exceeded %d retries without decreasing the cost", st.max_retries);
@@ -743,7 +748,7 @@ int ba_reduce_buffer(ba_engine* e, void** device_ptr, int64_t* n_doubles) {
 int ba_cost_buffer(ba_engine* e, void** device_ptr, int64_t* n_doubles) {
   if (!e || !device_ptr || !n_doubles) { set_error("null argument"); return BA_ERR_INVALID; }
   *device_ptr = e->cost_buf;
-  *n_doubles = 2;
+  *n_doubles = 4;
   return BA_OK;
 }
 
@@ -760,7 +765,7 @@ static int buffer_info(ba_engine* e, int id, const double** p, int64_t* n) {
     case BA_BUF_LINV: *p = e->LINV; *n = 6 * e->N; break;
     case BA_BUF_Z: *p = e->Z; *n = 3 * e->N; break;
     case BA_BUF_REDUCE: *p = e->red; *n = e->red_len; break;
-    case BA_BUF_COST: *p = e->cost_buf; *n = 2; break;
+    case BA_BUF_COST: *p = e->cost_buf; *n = 4; break;
     default: set_error("unknown buffer id %d", id); return BA_ERR_INVALID;
   }
   return BA_OK;

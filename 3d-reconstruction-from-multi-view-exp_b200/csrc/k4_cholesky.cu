@@ -33,6 +33,21 @@ __device__ __forceinline__ double rcp_newton(double d) {
   return r;
 }
 
+// First non-positive pivot of a panel, encoded so that atomicMin picks the lowest column: a pivot
+// that is exactly zero (or NaN) means a singular system -- the reference's LU raises
+// LinAlgError("Singular matrix") there (:146; e.g. a camera without observations has an all-zero
+// row) -- while a negative one is a system that damping can still repair: the step is rejected.
+// Only the first failing panel of a factorisation reports (later pivots are contaminated).
+constexpr int kNoBadPivot = 1 << 20;
+__device__ __forceinline__ int bad_pivot_code(int col, double d) {
+  return 2 * col + ((d == 0.0 || d != d) ? 1 : 0);
+}
+__device__ __forceinline__ void report_bad_pivot(ba_lm_state* ctl, int code) {
+  if (code == kNoBadPivot || ctl->chol_fail) return;
+  ctl->chol_fail = 1;
+  if ((code & 1) && ctl->status == BA_OK) ctl->status = BA_ERR_SINGULAR;
+}
+
 constexpr int kPanelThreads = 8 * NB;  // 4 threads per row of the tall panel (16 columns each)
 constexpr int kPanelCols = 16;          // columns per thread
 
@@ -49,7 +64,7 @@ chol_panel_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb,
   const int tid = threadIdx.x;
   // block 0 carries the rows of the identity (-> W = L_D^-T), block b >= 1 the 64 rows from rbase
   const int rbase = k0 + nb + ((int)blockIdx.x - 1) * NB;
-  if (tid == 0) s_fail = 0;
+  if (tid == 0) s_fail = kNoBadPivot;
   {
     // coalesced loads, all issued before the first use (L2 latency paid once)
     double vd[8], va[8];
@@ -123,7 +138,7 @@ chol_panel_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb,
   __syncthreads();
   if (tid < NB) {
     const double d = piv[tid];
-    if (tid < nb && !(d > 0.0)) s_fail = 1;
+    if (tid < nb && !(d > 0.0)) atomicMin(&s_fail, bad_pivot_code(tid, d));
     piv[tid] = rsqrt(d);  // = 1 / L[tid][tid]
   }
   __syncthreads();
@@ -131,7 +146,7 @@ chol_panel_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb,
     T[q >> 6][q & 63] *= piv[q & 63];
   __syncthreads();
   if (blockIdx.x == 0) {
-    if (tid == 0 && s_fail) ctl->chol_fail = 1;
+    if (tid == 0) report_bad_pivot(ctl, s_fail);
     // L_D (k-major) for the trailing update: Lt[m][k0 + r] = L_D[r][m]
     for (int q = tid; q < NB * NB; q += kPanelThreads) {
       const int m = q >> 6, rr = q & 63;
@@ -304,7 +319,7 @@ chol_step_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int
   double* sA = sB + NB * kSLD;            // [64][68] Lp[:, rbase ..]
   __shared__ int s_fail;
   const int rbase = k0 + nb + ((int)blockIdx.x - 1) * NB;
-  if (tid == 0) s_fail = 0;
+  if (tid == 0) s_fail = kNoBadPivot;
   {
     double vd[8], va[8];
     const int c = tid & 63;
@@ -397,14 +412,14 @@ chol_step_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int
   __syncthreads();
   if (tid < NB) {
     const double d = piv[tid];
-    if (tid < nb && !(d > 0.0)) s_fail = 1;
+    if (tid < nb && !(d > 0.0)) atomicMin(&s_fail, bad_pivot_code(tid, d));
     piv[tid] = rsqrt(d);
   }
   __syncthreads();
   for (int q = tid; q < 2 * NB * NB; q += kPanelThreads) T[q >> 6][q & 63] *= piv[q & 63];
   __syncthreads();
   if (blockIdx.x == 0) {
-    if (tid == 0 && s_fail) ctl->chol_fail = 1;
+    if (tid == 0) report_bad_pivot(ctl, s_fail);
     for (int q = tid; q < NB * NB; q += kPanelThreads) {
       const int m = q >> 6, rr = q & 63;
       if (m < nb && rr < nb) Lt[(size_t)m * ld + k0 + rr] = rr >= m ? T[rr][m] : 0.0;
@@ -493,15 +508,31 @@ chol_backsolve_kernel(const double* __restrict__ S, int ld, int n, int rhs_row,
 // depend on x, so they are fetched BEFORE the barrier and the HBM latency overlaps the wait.
 // One barrier per block; fixed summation order (deterministic).  All CTAs must be co-resident:
 // the grid never exceeds the SM count and the kernel runs alone on its stream.
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
+// The kernel is launched cooperatively (all CTAs co-resident or the launch fails), and the spin is
+// bounded as well: after kBarrierLimitNs the waiting CTA poisons the counter (every later barrier of
+// every CTA falls through) and raises BA_ERR_BARRIER in the control block instead of hanging the GPU.
+constexpr unsigned long long kBarrierLimitNs = 10ull * 1000000000ull;
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target, ba_lm_state* ctl) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(bar, 1u);
-    unsigned int v;
+    unsigned int v, polls = 0;
+    unsigned long long t0 = 0;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-    } while (v < target);
+      if (v >= target) break;
+      if ((++polls & 1023u) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > kBarrierLimitNs) {
+          atomicOr(bar, 0x80000000u);
+          ctl->status = BA_ERR_BARRIER;
+          break;
+        }
+      }
+    } while (true);
   }
   __syncthreads();
 }
@@ -509,7 +540,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
 __global__ void __launch_bounds__(256)
 chol_backsolve_grid_kernel(const double* __restrict__ S, int ld, int n, int rhs_row,
                            const double* __restrict__ W, double* __restrict__ ywork,
-                           double* __restrict__ dxi, unsigned int* bar, const ba_lm_state* ctl,
+                           double* __restrict__ dxi, unsigned int* bar, ba_lm_state* ctl,
                            int use_ctl) {
   if (use_ctl && ctl->done) return;
   __shared__ double xB[NB], yB[NB], part[4][NB];
@@ -531,7 +562,7 @@ chol_backsolve_grid_kernel(const double* __restrict__ S, int ld, int n, int rhs_
   };
   prefetch(nblk - 1, cta);
   unsigned int epoch = 0;
-  grid_barrier(bar, ++epoch * G);
+  grid_barrier(bar, ++epoch * G, ctl);
   for (int blk = nblk - 1; blk >= 0; --blk) {
     const int b0 = blk * NB;
     const int w = n - b0 < NB ? n - b0 : NB;
@@ -568,7 +599,7 @@ chol_backsolve_grid_kernel(const double* __restrict__ S, int ld, int n, int rhs_
       __syncthreads();
     }
     if (blk > 0) prefetch(blk - 1, cta);  // static data: in flight while the barrier is awaited
-    if (blk > 0) grid_barrier(bar, ++epoch * G);
+    if (blk > 0) grid_barrier(bar, ++epoch * G, ctl);
   }
 }
 
@@ -658,8 +689,21 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
     const int nblk = (n + NB - 1) / NB;
     const int G = nblk < e->num_sms ? nblk : e->num_sms;
     BA_CUDA(cudaMemsetAsync(e->chol_bar, 0, sizeof(unsigned int), s));
-    chol_backsolve_grid_kernel<<<G, 256, 0, s>>>(e->P(), ld, n, e->rhs_row, e->Winv, e->ywork, e->dxi,
-                                                 e->chol_bar, e->ctl, use_ctl);
+    // cooperative launch: the driver admits the grid only if all G CTAs can be resident together,
+    // whatever else the device is running (BA_CHOL_NO_COOP: plain launch, for A/B runs)
+    static const bool no_coop = std::getenv("BA_CHOL_NO_COOP") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(G);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_coop ? 0 : 1;
+    BA_CUDA(cudaLaunchKernelEx(&cfg, chol_backsolve_grid_kernel, (const double*)e->P(), ld, n, e->rhs_row,
+                               (const double*)e->Winv, e->ywork, e->dxi, e->chol_bar, e->ctl, use_ctl));
     BA_LAUNCH_CHECK();
     return BA_OK;
   }

@@ -183,7 +183,11 @@ __global__ void cost_finish2_kernel(const double* __restrict__ part, int n, doub
   double acc = 0.0;
   for (int k = threadIdx.x; k < n; k += blockDim.x) acc += part[k];
   const double tot = block_sum(acc, scratch);
-  if (threadIdx.x == 0) *out = tot;
+  if (threadIdx.x == 0) {
+    out[0] = tot;
+    // travels with the trial cost through whatever sums it over the ranks (see ba_cost_buffer)
+    out[1] = (use_ctl && ctl->status == BA_ERR_SINGULAR) ? 1.0 : 0.0;
+  }
 }
 
 int launch_update_trial(ba_engine* e, bool conditional, cudaStream_t s) {
@@ -255,7 +259,9 @@ __global__ void lm_decide_kernel(ba_lm_state* ctl, const double* cost_buf, ba_it
   ctl->E_trial = E_;
   ctl->solves += 1;
   ctl->iter_solves += 1;
-  if (ctl->status != BA_OK) {  // singular point block: stop, the host raises
+  // a singular point block on ANY rank (the flag is summed over the ranks with the cost)
+  if (cost_buf[2] > 0.0 && ctl->status == BA_OK) ctl->status = BA_ERR_SINGULAR;
+  if (ctl->status != BA_OK) {  // singular block / failed barrier: stop, the host raises
     ctl->done = 1;
     ctl->accepted = 0;
     return;

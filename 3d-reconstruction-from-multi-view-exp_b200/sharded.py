@@ -11,7 +11,7 @@ memory (``csrc/comm_peer.cu``), the loop is the single-engine CUDA-graph loop (`
 nothing of this module but ``shard_bounds`` is used.  The two exchanges:
 
   1. the partial reduced system  [sum_j Y_j Y_j^T | rhs row | U_i | dF_i]  (one flat buffer),
-  2. the trial cost (one double).
+  2. the trial cost and the singular-block flag (two doubles).
 
 After (1) every rank holds the same reduced camera system and factors it redundantly
 (replicated Cholesky), so the camera step, the accept/reject decision and the damping schedule
@@ -57,7 +57,10 @@ def lm_loop(engine, dist, group, scale_factor, delta_tol, max_iter, max_retries=
         engine.lm_phase_reduce()
         dist.all_reduce(red, group=group)
         engine.lm_phase_solve()
-        dist.all_reduce(cost[1:2], group=group)
+        # trial cost and the "singular point block" flag together: the rank that owns a singular
+        # block (reference :128 raises LinAlgError) must stop every rank in this very solve, or
+        # the others would wait for it in the next collective forever
+        dist.all_reduce(cost[1:3], group=group)
         engine.lm_phase_decide()
 
     if on_state is None and hasattr(engine, "lm_state_post"):
@@ -65,7 +68,8 @@ def lm_loop(engine, dist, group, scale_factor, delta_tol, max_iter, max_retries=
         # the control block of solve n is read, so the device never idles while the host
         # launches.  After termination every kernel of the extra solve is a no-op and the extra
         # all-reduces sum buffers that nobody reads again; `done` is identical on all ranks (it
-        # derives from all-reduced data), so all ranks issue the same collectives.
+        # derives from all-reduced data only: the cost and the summed singular flag), so all ranks
+        # issue the same collectives.
         enqueue_solve()
         engine.lm_state_post(0)
         n = 1

@@ -48,7 +48,8 @@ typedef enum ba_status {
   BA_ERR_NO_DEVICE = 5, /* no CUDA device           -> RuntimeError (there is no CPU path)  */
   BA_ERR_STALL = 6,     /* inner LM loop exceeded max_retries -> RuntimeError (the reference
                            loops forever, :118; documented deviation)                       */
-  BA_ERR_COMM = 7       /* a peer rank did not answer within the spin limit -> RuntimeError  */
+  BA_ERR_COMM = 7,      /* a peer rank did not answer within the spin limit -> RuntimeError  */
+  BA_ERR_BARRIER = 8    /* a grid-wide barrier inside one kernel timed out  -> RuntimeError  */
 } ba_status;
 
 enum { BA_MEM_HOST = 0, BA_MEM_DEVICE = 1 };
@@ -181,7 +182,10 @@ int ba_lm_records(ba_engine* e, ba_iter_record* records, int max_records, int* n
 /* ---- buffers the host all-reduces when points are sharded over ranks ----------------- */
 /* Partial reduced system: [P (n_pad x n_pad) | U (n_cams x 81) | dF (n_cams x 9)] doubles. */
 int ba_reduce_buffer(ba_engine* e, void** device_ptr, int64_t* n_doubles);
-/* [cost slot 0 (current / initial), cost slot 1 (trial)] doubles. */
+/* [cost slot 0 (current / initial), cost slot 1 (trial), 1.0 if a point block of this engine's
+ * shard was singular in the trial solve else 0.0, pad] doubles.  A host that sums the trial cost
+ * over the ranks sums elements 1..2 together, so that one rank's singular block (LinAlgError,
+ * reference :128) stops every rank in the same solve. */
 int ba_cost_buffer(ba_engine* e, void** device_ptr, int64_t* n_doubles);
 /* Only one rank prints/logs; every rank must still hold the same U/dF: this marks whether
  * this engine's U/dF partials are to be counted (all ranks: 1). */
@@ -222,7 +226,7 @@ typedef enum ba_buffer_id {
   BA_BUF_LINV = 8,   /* [n_points][6] inverse Cholesky factor of damped V_j     K2 */
   BA_BUF_Z = 9,      /* [n_points][3] L_j^-1 d_P_j                               K2 */
   BA_BUF_REDUCE = 10,/* the reduce buffer (see ba_reduce_buffer)                    */
-  BA_BUF_COST = 11   /* [2] cost of the current / initial state, cost of the trial  */
+  BA_BUF_COST = 11   /* [4] see ba_cost_buffer                                      */
 } ba_buffer_id;
 int ba_buffer_size(ba_engine* e, int id, int64_t* n_doubles);
 int ba_buffer_read(ba_engine* e, int id, double* host_out, int64_t n_doubles, void* stream);

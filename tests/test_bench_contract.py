@@ -1,12 +1,14 @@
-"""bench.py's reference arm runs on the host CPU (the oracle port is the reference's CPU path on a
-box where /root/reference does not exist): its JSON line is checked here against the contract the
-driver parses.  The CUDA arm's line is produced on the GPU box (`bench.py`, no flags)."""
+"""bench.py's reference arm runs on the host CPU (the unmodified reference class from the build-time
+copy oracle/_ref, or the oracle port where that copy was not built): its JSON line is checked here
+against the contract the driver parses.  The CUDA arm's line is produced on the GPU box (`bench.py`, no flags)."""
 import json
 import os
 import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 
 def test_reference_arm_prints_one_contract_line():
@@ -19,9 +21,13 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "observations/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
     assert d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None
-    assert "workload" in d["config"] and d["config"]["workload"].startswith("c2")
+    assert "workload" in d["config"] and d["config"]["workload"].startswith("c3")
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    # the unmodified reference (oracle/_ref, built where /root/reference exists) or else the port
+    from oracle import build_ref
+
+    assert cb["kind"] == ("reference" if build_ref.verify() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     e2e = d["e2e"]
     assert e2e["value"] == d["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
 
@@ -32,3 +38,17 @@ def test_reference_arm_under_torchrun_env_only_rank0_prints():
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT,
                          env=env)
     assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_reference_arm_is_not_pinned_to_one_thread_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm opens the pools up again (the
+    N > 1 reference lines were measured on one thread)."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--steps", "1", "--warmup", "0", "--workload", "c2"], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    ncpu = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == ncpu and d["n_gpus"] == 2 and d["scaling"] == "strong"
+    assert d["config"]["workload"].startswith("c2")

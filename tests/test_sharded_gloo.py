@@ -30,7 +30,7 @@ class OracleShardEngine:
         M = obs.n_cams
         self.M, self.nfull = M, 9 * M
         self._red = torch.zeros(self.nfull * self.nfull + self.nfull + 90 * M, dtype=torch.float64)
-        self._cost = torch.zeros(2, dtype=torch.float64)
+        self._cost = torch.zeros(4, dtype=torch.float64)  # as ba_cost_buffer: E0, E_trial, singular flag, pad
         self.st = types.SimpleNamespace()
         self.records = []
 
@@ -57,7 +57,14 @@ class OracleShardEngine:
         if s.need_linearize:
             self.lin = O.linearize(self.obs, self.X, self.f, self.u, self.R, self.t, self.f0)
         # local sum_j F^T E^-1 F and sum_j F^T E^-1 d_P (damped point blocks, undamped U)
-        A0, b0, self.Vinv = O.reduced_system(self.obs, self.lin, s.c)
+        try:
+            A0, b0, self.Vinv = O.reduced_system(self.obs, self.lin, s.c)
+        except np.linalg.LinAlgError:
+            # like the device: flag it, keep going with whatever the buffers hold; the flag is
+            # summed over the ranks with the trial cost and stops everybody in lm_phase_decide
+            s.status = 3  # BA_ERR_SINGULAR
+            self._red.zero_()
+            return
         Ud = np.zeros((n, n))
         for i in range(M):
             blk = self.lin.U[i].copy()
@@ -72,6 +79,10 @@ class OracleShardEngine:
         O, s, M, n = self.O, self.st, self.M, self.nfull
         if s.done:
             return
+        self._cost[2] = 1.0 if s.status == 3 else 0.0
+        if s.status == 3:
+            self._cost[1] = 0.0
+            return
         buf = self._red.numpy()
         P = buf[: n * n].reshape(n, n)
         rhsP = buf[n * n: n * n + n]
@@ -85,7 +96,10 @@ class OracleShardEngine:
         b = rhsP - gcam
         _, kept = O.gauge_indices(M, self.axis)
         dxi = np.zeros(n)
-        dxi[kept] = np.linalg.solve(A[np.ix_(kept, kept)], b[kept])
+        try:
+            dxi[kept] = np.linalg.solve(A[np.ix_(kept, kept)], b[kept])
+        except np.linalg.LinAlgError:  # a peer's singular block left a garbage system
+            dxi[:] = 0.0
         dxi = dxi.reshape(M, 9)
         obs, lin = self.obs, self.lin
         Fd = O._segment_sum(obs.pt, np.einsum("oab,ob->oa", lin.W, dxi[obs.cam]), obs.n_points)
@@ -102,6 +116,11 @@ class OracleShardEngine:
         s.E_trial = E_
         s.solves += 1
         s.iter_solves += 1
+        if float(self._cost[2]) > 0.0:
+            s.status = 3
+        if s.status != 0:
+            s.done, s.accepted = 1, 0
+            return
         if E_ > s.E:
             s.c *= s.scale
             s.accepted, s.need_linearize = 0, 0
@@ -176,3 +195,42 @@ def test_sharded_loop_reproduces_reference(tmp_path, world, case):
     # the point shards tile the scene
     spans = sorted(tuple(np.load(tmp_path / f"X_{r}.npy")[:2].astype(int)) for r in range(world))
     assert spans[0][0] == 0 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def _worker_singular(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import ba_b200
+        from conftest import case_inputs, load_golden
+        from oracle import ba_oracle as O
+
+        sharded = ba_b200.submodule("sharded")
+        g = load_golden("small_sparse_xup")
+        x, vis, X0, K0, R0, t0, axis, f0 = case_inputs(g)
+        vis = vis.copy()
+        vis[1, :] = False  # a point without any view, owned by rank 0: inv() raises there (:128)
+        obs = O.ObsList.from_dense(x, vis)
+        X, R, t = O.normalize_gauge(X0, R0, t0, axis)
+        f, u = K0[:, 0, 0].copy(), K0[:, :2, 2].copy()
+        lo, hi = sharded.shard_bounds(obs.n_points, world, obs.ptr)[rank]
+        assert (lo <= 1 < hi) == (rank == 0)
+        eng = OracleShardEngine(obs.subset_points(lo, hi), X[lo:hi], f, u, R, t, f0, axis)
+        st = sharded.lm_loop(eng, dist, None, 2.0, 1e-8, 100)
+        np.save(os.path.join(out_dir, f"st_{rank}.npy"), np.array([st.status, st.done, st.solves, st.count]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_singular_block_on_one_rank_stops_every_rank(tmp_path):
+    """with the collective exchange only the trial cost was summed, so the rank owning
+    a 0-view point stopped (LinAlgError) while its peers waited in the next all-reduce forever.
+    The singular flag now travels with the cost: every rank stops in the first solve."""
+    world = 2
+    mp.spawn(_worker_singular, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        status, done, solves, count = np.load(tmp_path / f"st_{r}.npy")
+        assert (status, done, solves, count) == (3, 1, 1, 0)
