@@ -6,11 +6,29 @@ the two buffers a sharded run all-reduces).
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
+import sys
+import weakref
 
 import numpy as np
 
 from . import _cabi
+
+# Engines still alive when the interpreter exits are destroyed from an atexit hook, i.e. while the
+# CUDA runtime is still up: an engine that is only collected during interpreter finalisation (the
+# reference scripts keep theirs in a module global) would call into a torn-down CUDA context from
+# __del__ -- a segmentation fault at exit.
+_live_engines: "weakref.WeakSet[Engine]" = weakref.WeakSet()
+
+
+@atexit.register
+def _close_live_engines():
+    for eng in list(_live_engines):
+        try:
+            eng.close()
+        except Exception:
+            pass
 
 
 def _current_stream(device: int) -> int:
@@ -64,6 +82,7 @@ class Engine:
         npad, nfull, rhs = C.c_int32(), C.c_int32(), C.c_int32()
         _cabi.check(self._lib.ba_reduced_layout(self._h, C.byref(npad), C.byref(nfull), C.byref(rhs)))
         self.n_pad, self.n_full, self.rhs_row = npad.value, nfull.value, rhs.value
+        _live_engines.add(self)
 
     # -- life cycle ---------------------------------------------------------------------------
     def close(self):
@@ -73,6 +92,8 @@ class Engine:
             self._h = None
 
     def __del__(self):
+        if sys is None or sys.is_finalizing():  # too late to talk to CUDA; the atexit hook ran already
+            return
         try:
             self.close()
         except Exception:
