@@ -268,6 +268,7 @@ int launch_camera_blocks(ba_engine* e, cudaStream_t s, bool conditional);
 int launch_k2b(ba_engine* e, bool conditional, double c_host, cudaStream_t s);
 int launch_k3(ba_engine* e, bool conditional, cudaStream_t s);
 int syrk_plan_engine(ba_engine* e);
+int syrk_feed_is_tma();  // 1: the 128-tile SYRK is fed by TMA + mbarriers, 0: by cp.async (BA_SYRK_NO_TMA)
 // Gram matrix P = Yt^T Yt of a k-major operand outside an engine (k3_schur_syrk.cu)
 struct GramWorkspace {
   int n_pad = 0, num_sms = 0, n_items = 0, n_tiles = 0;

@@ -831,6 +831,8 @@ int ba_profile_reset(ba_engine* e) {
 
 int ba_fp64_peak(int device, int use_dmma, double* tflops) { return fp64_peak(device, use_dmma, tflops); }
 
+int ba_syrk_feed(void) { return syrk_feed_is_tma(); }
+
 int ba_syrk_plan_info(int n_cams, int64_t n_points, int tile, int num_sms, int* n_items, int* n_tiles,
                       double* makespan_rows, double* ideal_rows) {
   return syrk_plan_selftest(n_cams, n_points, tile, num_sms, n_items, n_tiles, makespan_rows, ideal_rows);

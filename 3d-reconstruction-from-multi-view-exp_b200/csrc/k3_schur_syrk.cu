@@ -18,6 +18,8 @@
 // Compute roofline (FP64 tensor): algorithmic flops = 3N * n (n + 1), n = 9M - 7.
 //
 // Sparse visibility: see k3_schur_sparse.cu (output-stationary, no atomics).
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -251,6 +253,224 @@ syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_c
           make_double2(acc[i][j][0], acc[i][j][1]);
 }
 
+// ---- 128-tiles fed by TMA ------------------------------------------------------------------------
+// The same product with a Blackwell-native operand feed.  ncu on the cp.async kernel at C3: every
+// chunk starts with all 16 warps issuing their LDGSTS (128 warp instructions, ~8 LSU cycles each)
+// right behind the block barrier, and the fragment loads of the chunk's first k-steps queue behind
+// them in the same LSU pipe -- ~1000 of every 8192 cycles the FP64 tensor pipes wait (tiles without
+// ragged edges ran at 85 % of the DMMA peak).  Here one extra warp is the producer: per chunk it
+// arms the stage's `full` mbarrier with the byte count and issues the tensor copies
+// (cp.async.bulk.tensor.2d -> SASS UTMALDG); the TMA engine writes shared memory and completes the
+// barrier, no LSU instruction and no block barrier is involved.  The 16 consumer warps wait on
+// `full`, run their DMMAs, and release the stage through the `empty` mbarrier (one arrival per warp).
+//
+// Shared-memory layout per stage and operand: [16 column groups][KC k-rows][8 doubles] -- one TMA
+// box {8 columns, KC rows} per group, written densely.  A warp's fragment load (4 k-rows x 8
+// columns of one group) is then 256 contiguous bytes: two conflict-free wavefronts, no padding.
+// Columns beyond n_valid lie outside the tensor and are zero-filled by the TMA unit.
+constexpr int kTmaTile = 128, kTmaKC = 32, kTmaStages = 3, kTmaGroups = kTmaTile / 8;
+constexpr int kTmaConsumerWarps = 16;
+constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;
+constexpr int kTmaOperandDoubles = kTmaKC * kTmaTile;                  // 4096 doubles = 32 KB
+constexpr int kTmaGroupBytes = kTmaKC * 8 * (int)sizeof(double);       // 2 KB per box
+constexpr size_t kTmaSmemBytes = (size_t)kTmaStages * 2 * kTmaOperandDoubles * sizeof(double) + 128 /*alignment*/ + 64 /*barriers*/;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Wait for the phase of the given parity.  The spin is bounded: a copy that never lands (a wrong
+// byte count, a bad descriptor) becomes a trap -- a failed launch -- instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok = 0;
+  for (unsigned spins = 0; !ok; ++spins) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+template <bool SUB>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, int64_t n_chunks,
+                const SyrkItem* __restrict__ items, double* __restrict__ part, const ba_lm_state* ctl,
+                int n_store, SubSplit sp) {
+  if (ctl && ctl->done) return;
+  constexpr int TILE = kTmaTile, KC = kTmaKC, WR = 4, WC = 4;
+  constexpr int WM = TILE / WR, WN = TILE / WC, FM = WM / 8, FN = WN / 8;
+  extern __shared__ unsigned char smem_raw[];
+
+  int ti, tj;
+  int64_t c_lo, c_hi;
+  if (SUB) {
+    tile_from_linear(blockIdx.x, ti, tj);
+    if (sp.world > 1 && (sp.tile_row0 + ti) % sp.world != sp.rank) return;  // another rank's tile row
+    c_lo = 0;
+    c_hi = n_chunks;
+  } else {
+    const SyrkItem it = items[blockIdx.x];
+    ti = it.ti; tj = it.tj; c_lo = it.c_lo; c_hi = it.c_hi;
+  }
+  const bool diag = ti == tj;
+  const int nk = (int)(c_hi > c_lo ? c_hi - c_lo : 0);
+
+  // carve shared memory: operand stages (128-byte aligned for the TMA unit), then the mbarriers
+  const unsigned base = (smem_u32(smem_raw) + 127u) & ~127u;
+  double* stages = reinterpret_cast<double*>(smem_raw + (base - smem_u32(smem_raw)));
+  const unsigned bars = base + kTmaStages * 2 * kTmaOperandDoubles * (unsigned)sizeof(double);
+  auto full_bar = [&](int st) { return bars + 8u * st; };
+  auto empty_bar = [&](int st) { return bars + 8u * (kTmaStages + st); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // diagonal tiles: only the sub-tiles on or below the diagonal, dealt to warps 0..9 (see
+  // syrk_dmma_kernel); the other consumer warps leave at once and are not counted by `empty`
+  const int n_live = diag ? WR * (WR + 1) / 2 : kTmaConsumerWarps;
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < kTmaStages; ++st) {
+      mbar_init(full_bar(st), 1);
+      mbar_init(empty_bar(st), n_live);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kTmaConsumerWarps) {
+    // ---- producer warp: lane g < 16 copies column group g of A, lane 16 + g that of B -----------
+    const unsigned stage_bytes = (diag ? 1u : 2u) * kTmaOperandDoubles * (unsigned)sizeof(double);
+    const bool issuer = lane < kTmaGroups || !diag;
+    const int grp = lane & (kTmaGroups - 1);
+    const int col = (lane < kTmaGroups ? ti : tj) * TILE + 8 * grp;
+    const unsigned dst_off = (lane < kTmaGroups ? 0u : (unsigned)kTmaOperandDoubles * 8u) + (unsigned)grp * kTmaGroupBytes;
+    for (int kc = 0; kc < nk; ++kc) {
+      const int st = kc % kTmaStages;
+      const unsigned use = (unsigned)(kc / kTmaStages);
+      if (use > 0) mbar_wait(empty_bar(st), (use - 1) & 1u);  // the consumers are done with the previous use
+      if (lane == 0) mbar_arrive_expect_tx(full_bar(st), stage_bytes);
+      __syncwarp();
+      if (issuer)
+        tma_load_2d(base + (unsigned)st * 2u * kTmaOperandDoubles * 8u + dst_off, &tmap, col,
+                    (int)((c_lo + kc) * KC), full_bar(st));
+    }
+    return;
+  }
+
+  // ---- consumer warps -----------------------------------------------------------------------------
+  int wr = warp / WC, wc = warp % WC;
+  if (diag) {
+    if (warp >= n_live) return;
+    wr = 0;
+    while ((wr + 1) * (wr + 2) / 2 <= warp) ++wr;
+    wc = warp - wr * (wr + 1) / 2;
+  }
+  const int kq = lane & 3;
+  int vm = 0, vn = 0;
+#pragma unroll
+  for (int i = 0; i < FM; ++i) vm += (ti * TILE + wr * WM + 8 * i) < n_valid;
+#pragma unroll
+  for (int j = 0; j < FN; ++j) vn += (tj * TILE + wc * WN + 8 * j) < n_valid;
+  const bool full = vm == FM && vn == FN;
+  // element (k, column group g, column c) of a stage operand sits at (g * KC + k) * 8 + c
+  const int aoff = (wr * FM * KC + kq) * 8 + (lane >> 2);
+  const int boff = (wc * FN * KC + kq) * 8 + (lane >> 2);
+
+  double acc[FM][FN][2];
+#pragma unroll
+  for (int i = 0; i < FM; ++i)
+#pragma unroll
+    for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int kc = 0; kc < nk; ++kc) {
+    const int st = kc % kTmaStages;
+    mbar_wait(full_bar(st), (unsigned)(kc / kTmaStages) & 1u);
+    const double* a = stages + (size_t)st * 2 * kTmaOperandDoubles + aoff;
+    const double* b = stages + (size_t)st * 2 * kTmaOperandDoubles + (diag ? 0 : kTmaOperandDoubles) + boff;
+    if (full) {
+#pragma unroll
+      for (int kk = 0; kk < KC; kk += 4) {
+        double fa[FM], fb[FN];
+#pragma unroll
+        for (int i = 0; i < FM; ++i) fa[i] = a[(i * KC + kk) * 8];
+#pragma unroll
+        for (int j = 0; j < FN; ++j) fb[j] = b[(j * KC + kk) * 8];
+#pragma unroll
+        for (int i = 0; i < FM; ++i)
+#pragma unroll
+          for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+      }
+    } else if (vm > 0 && vn > 0) {
+#pragma unroll
+      for (int kk = 0; kk < KC; kk += 4) {
+        double fa[FM], fb[FN];
+#pragma unroll
+        for (int i = 0; i < FM; ++i) fa[i] = a[(i * KC + kk) * 8];
+#pragma unroll
+        for (int j = 0; j < FN; ++j) fb[j] = b[(j * KC + kk) * 8];
+#pragma unroll
+        for (int i = 0; i < FM; ++i)
+#pragma unroll
+          for (int j = 0; j < FN; ++j)
+            if (i < vm && j < vn) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar(st));  // this warp has read the stage
+  }
+
+  const int orow = wr * WM + (lane >> 2);
+  const int ocol = wc * WN + 2 * (lane & 3);
+  if (SUB) {
+    // S -= acc on the lower triangle; an accumulator pair sits at (r, c), (r, c + 1), c even
+#pragma unroll
+    for (int i = 0; i < FM; ++i)
+#pragma unroll
+      for (int j = 0; j < FN; ++j) {
+        const int r = ti * TILE + orow + 8 * i, c = tj * TILE + ocol + 8 * j;
+        if (r >= n_store || c > r) continue;
+        const size_t off = (size_t)r * ld + c;
+        double* p = part + off;
+        const bool push = sp.world > 1 && tj * TILE < sp.push_cols;
+        if (c + 1 <= r) {
+          double2 v = *reinterpret_cast<double2*>(p);
+          v.x -= acc[i][j][0];
+          v.y -= acc[i][j][1];
+          *reinterpret_cast<double2*>(p) = v;
+          if (push)
+            for (int q = 0; q < sp.world; ++q)
+              if (q != sp.rank) *reinterpret_cast<double2*>(sp.peer[q] + off) = v;
+        } else {
+          const double v = *p - acc[i][j][0];
+          *p = v;
+          if (push)
+            for (int q = 0; q < sp.world; ++q)
+              if (q != sp.rank) sp.peer[q][off] = v;
+        }
+      }
+    return;
+  }
+  double* out = part + (size_t)blockIdx.x * TILE * TILE;
+#pragma unroll
+  for (int i = 0; i < FM; ++i)
+#pragma unroll
+    for (int j = 0; j < FN; ++j)
+      *reinterpret_cast<double2*>(out + (size_t)(orow + 8 * i) * TILE + ocol + 8 * j) =
+          make_double2(acc[i][j][0], acc[i][j][1]);
+}
+
 // P[tile] = sum of the tile's items in a fixed order (ascending k range), restricted to the valid
 // part of P and, on diagonal tiles, to the pairs that touch the lower triangle.
 template <int TILE>
@@ -303,6 +523,8 @@ __global__ void stage_camera_blocks_kernel(int n, const double* __restrict__ src
 static inline int syrk_kc(int tile) { return tile == 128 ? 32 : 16; }
 static inline int syrk_occupancy(int tile) { return tile == 128 ? 1 : 4; }
 
+int syrk_feed_is_tma();
+
 // Relative duration of a tile per k-row (1 = full tile), mirroring the kernel's warp mapping:
 // edge tiles skip the 8x8 fragments beyond n_valid, diagonal tiles the sub-tiles above the
 // diagonal.  A warp sits on scheduler partition (warp % 4) with its own FP64 pipe: a CTA that has
@@ -336,7 +558,9 @@ static double tile_weight(int TILE, int WR, int WC, int occ, int ti, int tj, int
   // Measured at C2 (50 x 10k): the 64-tile kernel (four CTAs per SM) is fastest with uniform cuts
   // (floor 1.0: 0.302 ms per iteration, 0.75: 0.309, 0.5: 0.344, 0.35: 0.430); the 128-tile
   // kernel with floor 0.75 (1.0: 0.326, 0.75: 0.283, 0.5: 0.343, 0.35: 0.355).
-  double floor_w = occ == 1 ? 0.75 : 1.0;
+  // The TMA-fed kernel has no per-row copy instructions to pay for: a thin tile costs what its
+  // fragments cost, down to the rate at which the TMA unit streams the rows (measured floor ~0.3).
+  double floor_w = occ == 1 ? (syrk_feed_is_tma() ? 0.3 : 0.75) : 1.0;
   if (const char* f = std::getenv("BA_SYRK_FLOOR")) floor_w = std::atof(f);  // tuning experiments only
   return w > floor_w ? w : floor_w;
 }
@@ -465,13 +689,68 @@ int syrk_plan_engine(ba_engine* e) {
   return BA_OK;
 }
 
+// ---- tensor maps (host) ---------------------------------------------------------------------------
+// cuTensorMapEncodeTiled comes from the driver; it is fetched through the runtime so that the
+// library does not link against libcuda (the build container has no driver).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// k-major operand `base` [rows][ld] doubles, `cols` valid columns: boxes of 8 columns x kTmaKC rows.
+static int make_operand_map(CUtensorMap* map, const double* base, int cols, int64_t rows, int ld) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return BA_ERR_CUDA; }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
+  const cuuint32_t box[2] = {8, (cuuint32_t)kTmaKC};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box,
+                         estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for a %d x %lld operand, ld %d", (int)r, cols, (long long)rows, ld);
+    return BA_ERR_CUDA;
+  }
+  return BA_OK;
+}
+
+// BA_SYRK_NO_TMA=1 keeps the cp.async kernel (A/B timing).
+static bool syrk_use_tma() {
+  static const bool on = std::getenv("BA_SYRK_NO_TMA") == nullptr;
+  return on;
+}
+
+int syrk_feed_is_tma() { return syrk_use_tma() && tensor_map_encoder() != nullptr; }
+
 template <int TILE, int WR, int WC, int KC>
 static int launch_syrk(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
   const int64_t n_chunks = e->k_pad / KC;
-  const size_t smem = (size_t)2 * kStages * KC * (TILE + 4) * sizeof(double);
-  BA_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<TILE, WR, WC, KC, false>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  {
+  if (TILE == kTmaTile && KC == kTmaKC && syrk_use_tma()) {
+    CUtensorMap map;
+    BA_TRY(make_operand_map(&map, e->Yt, e->n_pad, e->k_pad, e->n_pad));
+    BA_CUDA(cudaFuncSetAttribute(syrk_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kTmaSmemBytes));
+    ProfScope ps(e, PG_SYRK, s);
+    syrk_tma_kernel<false><<<e->syrk_n_items, kTmaThreads, kTmaSmemBytes, s>>>(
+        map, e->n_pad, e->n_pad, n_chunks, e->syrk_items, e->Spart, ctl, 0, SubSplit{0, 1, 0, 0, {}});
+    BA_LAUNCH_CHECK();
+  } else {
+    const size_t smem = (size_t)2 * kStages * KC * (TILE + 4) * sizeof(double);
+    BA_CUDA(cudaFuncSetAttribute(syrk_dmma_kernel<TILE, WR, WC, KC, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope ps(e, PG_SYRK, s);
     syrk_dmma_kernel<TILE, WR, WC, KC, false><<<e->syrk_n_items, WR * WC * 32, smem, s>>>(
         e->Yt, e->n_pad, e->n_pad, n_chunks, e->syrk_items, e->Spart, ctl, 0, SubSplit{0, 1, 0, 0, {}});
@@ -511,6 +790,16 @@ static int launch_syrk_sub(double* S, int ld, int n_rows, int t0, const double* 
     sp.tile_row0 = t0 / TILE;
     sp.push_cols = split->push_cols;
     for (int q = 0; q < split->world; ++q) sp.peer[q] = split->S_peer[q] + origin;
+  }
+  if (TILE == kTmaTile && KC == kTmaKC && syrk_use_tma()) {
+    CUtensorMap map;
+    BA_TRY(make_operand_map(&map, Lt + t0, n_valid, depth, ld));
+    BA_CUDA(cudaFuncSetAttribute(syrk_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kTmaSmemBytes));
+    syrk_tma_kernel<true><<<n_tiles, kTmaThreads, kTmaSmemBytes, s>>>(map, ld, n_valid, n_chunks, nullptr,
+                                                                      S + origin, ctl, n_store, sp);
+    BA_LAUNCH_CHECK();
+    return BA_OK;
   }
   syrk_dmma_kernel<TILE, WR, WC, KC, true><<<n_tiles, WR * WC * 32, smem, s>>>(
       Lt + t0, ld, n_valid, n_chunks, nullptr, S + origin, ctl, n_store, sp);

@@ -316,3 +316,8 @@ def fp64_peak(device: int = 0, dmma: bool = True) -> float:
     v = C.c_double()
     _cabi.check(_cabi.load().ba_fp64_peak(device, 1 if dmma else 0, C.byref(v)))
     return v.value
+
+
+def syrk_feed() -> str:
+    """Operand feed of the 128-tile SYRK kernel: "tma" (cp.async.bulk.tensor + mbarriers) or "cp.async"."""
+    return "tma" if _cabi.load().ba_syrk_feed() else "cp.async"

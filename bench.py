@@ -55,8 +55,10 @@ E2E_REPS = 3
 CHUNK = 10  # LM iterations per run from the perturbed start (see run_iters)
 # bounded CPU samples: points of the named scene (cameras unchanged).  REF_* for the unmodified
 # reference ((N, n, n) float64 temporary: 1.6 MB / 25.7 MB / 647 MB per point), PORT_* for the port
-REF_SAMPLE = {"c2": 1_000, "c3": 60, "c4": 6, "c5": 6}
-PORT_SAMPLE = {"c2": (10_000, 2), "c3": (1_500, 1), "c4": (4_000, 1), "c5": (4_000, 1)}
+# c4 / c5: no sample -- at 10 % visibility every camera needs some hundred points before it is seen at
+# all (an unseen camera makes the reference's reduced system singular, :146), and 100 points are 65 GB
+REF_SAMPLE = {"c2": 1_000, "c3": 60, "c4": None, "c5": None}
+PORT_SAMPLE = {"c2": (10_000, 2), "c3": (1_500, 1), "c4": (20_000, 1), "c5": (20_000, 1)}
 
 
 def parse_args():
@@ -243,7 +245,11 @@ def reference_run(name: str, n_points: int, calls):
             "points": sc.n_points}
 
 
-def reference_available() -> bool:
+def reference_available(name: str = "c3") -> bool:
+    """The unmodified reference can be timed: oracle/_ref is intact and the workload has a sample
+    the reference can hold."""
+    if REF_SAMPLE.get(name) is None:
+        return False
     try:
         from oracle import build_ref
 
@@ -261,7 +267,7 @@ def cpu_baseline_leg(name: str, budget_iters: int = 8) -> dict:
     port = oracle_port_run(name, n_pts, iters)
     port_desc = (f"{port['iterations']} LM iteration(s) of the CPU oracle port on the first {port['points']} points "
                  f"({port['observations']} observations) in {port['seconds']:.1f} s; {port['formulation']}")
-    if reference_available():
+    if reference_available(name):
         ref = reference_run(name, REF_SAMPLE[name], [budget_iters])
         return {"value": ref["value"], "unit": UNIT, "cores": cores, "kind": "reference",
                 "sample": f"{ref['iterations']} LM iterations of the unmodified reference class (oracle/_ref) on the "
@@ -282,7 +288,7 @@ def run_reference(args, rank: int):
     cfg = workload_config(name)
     K, W = args.steps, max(args.warmup, 0)
     calls = [min(CHUNK, K - k0) for k0 in range(0, K, CHUNK)]
-    if reference_available():
+    if reference_available(name):
         if W > 0:
             reference_run(name, REF_SAMPLE[name], [W])
         res = reference_run(name, REF_SAMPLE[name], calls)
@@ -296,10 +302,13 @@ def run_reference(args, rank: int):
         n_pts, _ = PORT_SAMPLE[name]
         if W > 0:
             oracle_port_run(name, n_pts, 1)
-        res = oracle_port_run(name, n_pts, K)
+        res = oracle_port_run(name, n_pts, K if REF_SAMPLE.get(name) is not None else min(K, 3))
         kind = "port"
         sample = (f"{res['iterations']} LM iterations of the CPU oracle port on the first {res['points']} points "
-                  f"({res['observations']} observations) of {name}; {res['formulation']}; {cores} cores")
+                  f"({res['observations']} observations) of {name}; {res['formulation']}; {cores} cores"
+                  + ("" if REF_SAMPLE.get(name) is not None else
+                     "; the unmodified reference cannot hold a 1000-camera sample in which every camera is seen "
+                     "(647 MB per point, singular system otherwise)"))
     out = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["seconds"] / max(res["iterations"], 1) * 1e3,
@@ -557,6 +566,7 @@ def measure(ctx: Ctx, name: str, strong: bool, K: int, W: int, *, full_run_tol=N
             "kernel": kernel, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": None, "algorithmic_flops_per_launch": flops,
             "avg_launch_ms": avg_ms, "share_of_step": share,
+            "operand_feed": ctx.engine_mod.syrk_feed() if sc.dense else None,
             "peak_source": "measured live: register-resident DMMA.8x8x4 loop (ba_fp64_peak); "
                            "MEASURED_PEAKS.json has no FP64 figure",
         }
@@ -726,7 +736,11 @@ def run_cuda(args, rank: int, world: int, local_rank: int):
 
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline_leg(name)
+            try:
+                out["cpu_baseline"] = cpu_baseline_leg(name)
+            except Exception as exc:  # the CPU leg must never cost the GPU line
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "failed",
+                                       "sample": f"{type(exc).__name__}: {exc}"}
         for key, res in extra.items():
             wl = key.split("_")[0]
             if wl in ("c4", "c5") and not args.no_cpu_baseline:

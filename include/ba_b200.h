@@ -245,6 +245,10 @@ int ba_profile_get(ba_engine* e, const char* group, double* total_ms, int64_t* l
 int ba_profile_reset(ba_engine* e);
 /* FP64 peak micro-benchmarks (register-resident DMMA.8x8x4 / DFMA loops): TFLOP/s. */
 int ba_fp64_peak(int device, int use_dmma, double* tflops);
+/* How the 128-tile Schur SYRK / Cholesky trailing update gets its operands: 1 = TMA tensor copies +
+ * mbarriers with a producer warp (cp.async.bulk.tensor, SASS UTMALDG), 0 = cp.async (LDGSTS; set
+ * BA_SYRK_NO_TMA=1 for A/B timing, or the driver does not offer cuTensorMapEncodeTiled). */
+int ba_syrk_feed(void);
 /* Host-only (no device): plan the dense Schur product (K3) of an n_cams x n_points scene for a GPU
  * with num_sms SMs and `tile` = 64 or 128, verify that the work items cover every tile's K range
  * exactly once, and report the number of items / tiles and the modelled schedule length against

@@ -58,9 +58,10 @@ def _worker(rank, world, port, case, out_dir, exchange="collective", per_rank_gp
         full = adjuster.ObservationList.from_dense(x, vis)
         lo, hi = sharded.shard_bounds(full.n_points, world, full.obs_ptr)[rank]
         a, b = int(full.obs_ptr[lo]), int(full.obs_ptr[hi])
+        xy = full.obs_xy if full.obs_xy is not None else np.ascontiguousarray(full.dense_x).reshape(-1, 2)
         adj = ba_b200.BundleAdjuster.from_observations(
             full.obs_ptr[lo:hi + 1] - full.obs_ptr[lo],
-            None if full.dense else full.obs_cam[a:b], full.obs_xy[a:b],
+            None if full.dense else full.obs_cam[a:b], xy[a:b],
             X0[lo:hi], K0, R0, t0, f0=f0, axis=axis, dense=full.dense, device=dev,
             process_group=dist.group.WORLD, exchange=exchange)
         assert adj._peer_exchange == (exchange == "peer")

@@ -47,5 +47,5 @@ ms = prof["syrk"]["ms"] / prof["syrk"]["launches"]
 peak = ba_b200.submodule("engine").fp64_peak(0, True)
 print(json.dumps({"tag": args.tag, "cams": M, "points": N, "n_pad": eng.n_pad, "syrk_ms": ms,
                   "k3_ms": prof["k3"]["ms"] / args.reps, "k2_ms": prof["k2"]["ms"] / args.reps,
-                  "tflops": flops / ms / 1e9, "peak": peak, "frac": flops / ms / 1e9 / peak,
+                  "tflops": flops / ms / 1e9, "peak": peak, "feed": ba_b200.submodule("engine").syrk_feed(), "frac": flops / ms / 1e9 / peak,
                   "env": {k: v for k, v in os.environ.items() if k.startswith("BA_")}}))
