@@ -200,10 +200,13 @@ class BundleAdjuster:
 
 
 def _default_device() -> int:
-    try:
-        import torch
+    """torch's current device if the caller already uses torch with CUDA up, else device 0 (torch
+    is never imported from here, see ``engine._current_stream``)."""
+    import sys
 
-        if torch.cuda.is_available() and torch.cuda.is_initialized():
+    torch = sys.modules.get("torch")
+    try:
+        if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
             return int(torch.cuda.current_device())
     except Exception:  # pragma: no cover
         pass

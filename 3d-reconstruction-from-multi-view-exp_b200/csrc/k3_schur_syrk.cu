@@ -530,7 +530,7 @@ int syrk_feed_is_tma();
 // diagonal.  A warp sits on scheduler partition (warp % 4) with its own FP64 pipe: a CTA that has
 // an SM to itself takes as long as its busiest partition; with several CTAs per SM the partitions
 // even out and the mean counts.
-static double tile_weight(int TILE, int WR, int WC, int occ, int ti, int tj, int n_valid) {
+static double tile_weight(int TILE, int WR, int WC, int occ, int ti, int tj, int n_valid, int64_t k_pad = 0) {
   const int WM = TILE / WR, WN = TILE / WC, FM = WM / 8, FN = WN / 8;
   double load[4] = {0, 0, 0, 0};
   for (int warp = 0; warp < WR * WC; ++warp) {
@@ -560,7 +560,12 @@ static double tile_weight(int TILE, int WR, int WC, int occ, int ti, int tj, int
   // kernel with floor 0.75 (1.0: 0.326, 0.75: 0.283, 0.5: 0.343, 0.35: 0.355).
   // The TMA-fed kernel has no per-row copy instructions to pay for: a thin tile costs what its
   // fragments cost, down to the rate at which the TMA unit streams the rows (measured floor ~0.3).
-  double floor_w = occ == 1 ? (syrk_feed_is_tma() ? 0.3 : 0.75) : 1.0;
+  // Measured with the TMA kernel (B200): C3 (4.3 GB operand, ~3300-row pieces) floor 0.5: 28.79 ms,
+  // 0.3: 28.86, 0.15: 28.86, 0.75: 29.42; C2 (108 MB operand, two waves of ~730-row pieces) floor
+  // 1.0: 0.286 ms, 0.5: 0.298, 0.3: 0.311 -- with two waves the schedule is decided by whole items,
+  // and uniform cuts pack them best.
+  const bool small_operand = k_pad > 0 && (double)k_pad * n_valid * 8.0 <= 256.0 * 1024 * 1024;
+  double floor_w = occ == 1 ? (syrk_feed_is_tma() ? (small_operand ? 1.0 : 0.5) : 0.75) : 1.0;
   if (const char* f = std::getenv("BA_SYRK_FLOOR")) floor_w = std::atof(f);  // tuning experiments only
   return w > floor_w ? w : floor_w;
 }
@@ -587,7 +592,7 @@ static SyrkPlan plan_syrk(int n_pad, int TILE, int WR, int WC, int64_t k_pad, in
   const int slots = num_sms * occ;
   std::vector<double> w(n_tiles);
   for (int t = 0, ti = 0; ti < nt1; ++ti)
-    for (int tj = 0; tj <= ti; ++tj, ++t) w[t] = tile_weight(TILE, WR, WC, occ, ti, tj, n_pad);
+    for (int tj = 0; tj <= ti; ++tj, ++t) w[t] = tile_weight(TILE, WR, WC, occ, ti, tj, n_pad, k_pad);
   const int64_t min_chunks = std::max<int64_t>(1, 512 / KC);
   const int64_t s_max = std::max<int64_t>(1, n_chunks / min_chunks);
   const int64_t slab_cap = (int64_t)48 << 20;
@@ -902,7 +907,7 @@ int syrk_plan_selftest(int n_cams, int64_t n_points, int tile, int num_sms, int*
     if (pos != n_chunks) { set_error("plan: tile %d ends at chunk %lld of %lld", t, (long long)pos, (long long)n_chunks); return BA_ERR_STATE; }
     int ti = 0;
     while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    work += tile_weight(tile, tile == 128 ? 4 : 2, tile == 128 ? 4 : 2, syrk_occupancy(tile), ti, t - ti * (ti + 1) / 2, n_pad) * (double)k_pad;
+    work += tile_weight(tile, tile == 128 ? 4 : 2, tile == 128 ? 4 : 2, syrk_occupancy(tile), ti, t - ti * (ti + 1) / 2, n_pad, k_pad) * (double)k_pad;
   }
   if (n_items) *n_items = (int)plan.items.size();
   if (n_tiles) *n_tiles = nt;

@@ -32,13 +32,16 @@ def _close_live_engines():
 
 
 def _current_stream(device: int) -> int:
-    """torch's current CUDA stream on `device` if torch has CUDA up, else the default stream."""
+    """torch's current CUDA stream on `device` if the CALLER already uses torch with CUDA up, else
+    the default stream.  torch is never imported from here: a caller that has not imported it (the
+    reference scripts) cannot have a torch stream current, the import costs seconds, and an import
+    that fails half-way (e.g. under a stub `matplotlib` whose modules answer every attribute) leaves
+    extension modules behind that crash the interpreter at exit."""
+    torch = sys.modules.get("torch")
     try:
-        import torch
-
-        if torch.cuda.is_available() and torch.cuda.is_initialized():
+        if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
             return int(torch.cuda.current_stream(device).cuda_stream)
-    except Exception:  # pragma: no cover - torch absent or broken: default stream
+    except Exception:  # pragma: no cover - a broken torch: default stream
         pass
     return 0
 

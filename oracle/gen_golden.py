@@ -40,9 +40,17 @@ def _stub_matplotlib():
         def __iter__(self):
             return iter(())
 
+    def _plt_getattr(name):
+        # a stub must not answer dunder look-ups (__file__, __path__, __spec__ ...): code that walks
+        # sys.modules -- inspect.getmodule during `import torch`, for one -- would take the answers
+        # for real ones
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Anything()
+
     mpl = types.ModuleType("matplotlib")
     plt = types.ModuleType("matplotlib.pyplot")
-    plt.__getattr__ = lambda name: _Anything()  # type: ignore[attr-defined]
+    plt.__getattr__ = _plt_getattr  # type: ignore[attr-defined]
     plt.fignum_exists = lambda *_: False  # ends lib/visualization.py:175's loop at once
     mpl.pyplot = plt
     sys.modules.setdefault("matplotlib", mpl)

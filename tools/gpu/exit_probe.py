@@ -23,8 +23,16 @@ def stub_matplotlib():
         def __iter__(self):
             return iter(())
 
+    def _plt_getattr(name):
+        # a stub must not answer dunder look-ups (__file__, __path__, __spec__ ...): code that walks
+        # sys.modules -- inspect.getmodule during `import torch`, for one -- would take the answers
+        # for real ones
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Anything()
+
     mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
-    plt.__getattr__ = lambda name: _Anything()
+    plt.__getattr__ = _plt_getattr
     plt.fignum_exists = lambda *_: False
     mpl.pyplot = plt
     sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
@@ -75,4 +83,36 @@ elif mode == "ba_small_no_torch":
     with contextlib.redirect_stdout(io.StringIO()):
         adj.optimize(2.0, 1e-8, max_iter=5)
     print("records", len(adj.records), flush=True)
+elif mode == "script_trace":
+    # the unmodified script on the engine, with every call into the script / the reference modules /
+    # this package printed as it happens: the last line before a crash localises it
+    import runpy
+
+    pkg = os.path.join(ROOT, "3d-reconstruction-from-multi-view-exp_b200")
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    depth = [0]
+
+    def tracer(frame, event, arg):
+        fn = frame.f_code.co_filename
+        if event in ("call", "return") and (fn.startswith(ref) or fn.startswith(pkg)):
+            if event == "call":
+                print("  " * depth[0] + f"> {os.path.relpath(fn, ROOT)}:{frame.f_code.co_name}", flush=True)
+                depth[0] += 1
+            else:
+                depth[0] -= 1
+        elif event == "c_call" and getattr(arg, "__name__", "").startswith("ba_"):
+            print("  " * depth[0] + f"c> {arg.__name__}", flush=True)
+
+    stub_matplotlib()
+    sys.path[:0] = [pkg, ref]
+    sys.setprofile(tracer)
+    try:
+        runpy.run_path(os.path.join(ref, "euclidiean_reconstruction.py"), run_name="__main__")
+    finally:
+        sys.setprofile(None)
+    print("script returned", flush=True)
+    import gc
+
+    gc.collect()
+    print("gc done", flush=True)
 print("end of main", flush=True)

@@ -29,8 +29,16 @@ except ImportError:
         def __iter__(self):
             return iter(())
 
+    def _plt_getattr(name):
+        # a stub must not answer dunder look-ups (__file__, __path__, __spec__ ...): code that walks
+        # sys.modules -- inspect.getmodule during `import torch`, for one -- would take the answers
+        # for real ones
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Anything()
+
     mpl, plt = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
-    plt.__getattr__ = lambda name: _Anything()
+    plt.__getattr__ = _plt_getattr
     plt.fignum_exists = lambda *_: False
     mpl.pyplot = plt
     sys.modules["matplotlib"], sys.modules["matplotlib.pyplot"] = mpl, plt
