@@ -18,7 +18,8 @@ def __getattr__(name):
         from . import projection
 
         return getattr(projection, name)
-    if name in ("projective_depth_primary", "compute_projective_depth_primary_method"):
+    if name in ("projective_depth_primary", "compute_projective_depth_primary_method", "projective_depth_dual",
+                "compute_projective_depth_dual_method", "factorize_rank4", "factorization_method"):
         from . import projective_depth
 
         return getattr(projective_depth, name)

@@ -433,9 +433,594 @@ __global__ void depth_error_kernel(const double* __restrict__ part, int n, doubl
   if (threadIdx.x == 0) *out = f0 * sqrt(tot / count);  // :56
 }
 
+
+// ==================================================================================================
+// Dual method (reference :147-235) and the rank-4 factorisation (lib/factorization.py:5-15)
+// ==================================================================================================
+// Per pass the reference normalises W per IMAGE (:171-176), takes the four leading RIGHT singular
+// vectors V_ (N x 4, :178-181) and solves, per image, the N x N eigenproblem of
+//   B_i[j][l] = (v_j . v_l)(x_ij . x_il) / (|x_ij| |x_il|)                       (:183-204)
+// -- an (n_images, n_points, n_points) array (:188), the O(M N^2) memory that keeps the method from
+// large scenes.  B_i = C_i C_i^T with the N x 12 matrix C_i[j][(a, b)] = v_j[a] xhat_ij[b], so its
+// leading eigenvector is C_i w / |C_i w| with w the leading eigenvector of the 12 x 12 matrix
+// C_i^T C_i = sum_j (v_j v_j^T) (x) (xhat_ij xhat_ij^T); and V_ enters only through V_ V_^T, so any
+// orthonormal basis of the leading right singular subspace will do: V4 = Wn U4 L^-T with
+// U4 = basis of the leading eigenspace of G = Wn^T Wn (3M x 3M, tensor-core SYRK) and L L^T =
+// U4^T G U4.  Memory is O(M N) throughout.
+//   dual_norm_kernel       per-warp partials of the per-image squared norms of x z
+//   colsum_finish_kernel   fixed-order sums of per-warp partials (all per-image reductions)
+//   dual_scale_kernel      Wn = x z / norm2_i  (k-major, row = point)
+//   Gram + subspace_eig    as in the primary method
+//   dual_small_kernel      T = U4^T G U4, Cholesky, L^-1
+//   dual_v_kernel          warp per point: c = U4^T wn_j, v_j = L^-1 c, reprojection-error share
+//   dual_outer_kernel      per image sum_j (v v^T) (x) (xhat xhat^T): 10 x 6 unique products
+//   dual_eig12_kernel      thread per image: cyclic Jacobi on the 12 x 12 matrix, leading eigenvector
+//   dual_e_kernel          e_ij = sum v_j[a] xhat_ij[b] w_i[a, b]; per-image sum e^2, sum e
+//   dual_z_kernel          xi = e / |e_i| with each image's sum made non-negative (the sign LAPACK
+//                          leaves open, see oracle/depth_oracle.py), then the reference's row rule
+//                          (:212-215) and z = xi / |x|  (:218)
+constexpr int kMaxImageSlots = 2;  // images per lane: n_images <= 64
+
+__device__ __forceinline__ int64_t warp_global() { return ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; }
+__device__ __forceinline__ int64_t warps_total() { return ((int64_t)gridDim.x * blockDim.x) >> 5; }
+
+__global__ void __launch_bounds__(256)
+dual_norm_kernel(int64_t N, int M, const double* __restrict__ x, const double* __restrict__ z,
+                 double* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = warp_global(), nw = warps_total();
+  for (int s = 0; s * 32 < M; ++s) {
+    const int i = lane + 32 * s;
+    double acc = 0.0;
+    if (i < M)
+      for (int64_t j = w; j < N; j += nw) {
+        const double* xv = x + ((size_t)j * M + i) * 3;
+        const double zz = z[(size_t)j * M + i];
+        const double a = xv[0] * zz, b = xv[1] * zz, c = xv[2] * zz;
+        acc += a * a + b * b + c * c;
+      }
+    if (i < M) part[(size_t)w * M + i] = acc;
+  }
+}
+
+// out[k] = sum_r part[r][k], r ascending (deterministic), k < width
+__global__ void colsum_finish_kernel(const double* __restrict__ part, int64_t rows, int width,
+                                     double* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= width) return;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int64_t r = 0;
+  for (; r + 3 < rows; r += 4) {
+    a0 += part[(size_t)r * width + k];
+    a1 += part[(size_t)(r + 1) * width + k];
+    a2 += part[(size_t)(r + 2) * width + k];
+    a3 += part[(size_t)(r + 3) * width + k];
+  }
+  for (; r < rows; ++r) a0 += part[(size_t)r * width + k];
+  out[k] = (a0 + a1) + (a2 + a3);
+}
+
+__global__ void __launch_bounds__(256)
+dual_scale_kernel(int64_t N, int M, int ld, const double* __restrict__ x, const double* __restrict__ z,
+                  const double* __restrict__ norm2, double* __restrict__ Wn) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = warps_total();
+  for (int64_t j = warp_global(); j < N; j += nw) {
+    const double* xj = x + (size_t)j * M * 3;
+    const double* zj = z + (size_t)j * M;
+    double* out = Wn + (size_t)j * ld;
+    for (int a = lane; a < ld; a += 32) out[a] = a < 3 * M ? (xj[a] * zj[a / 3]) / norm2[a / 3] : 0.0;  // :171-176
+  }
+}
+
+// Plain copy of W (k-major) into the padded operand of the Gram kernel (factorisation).
+__global__ void __launch_bounds__(256)
+pad_rows_kernel(int64_t N, int n, int ld, const double* __restrict__ W, double* __restrict__ Wk) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = warps_total();
+  for (int64_t j = warp_global(); j < N; j += nw)
+    for (int a = lane; a < ld; a += 32) Wk[(size_t)j * ld + a] = a < n ? W[(size_t)j * n + a] : 0.0;
+}
+
+// Cyclic Jacobi on a symmetric K x K matrix held by ONE thread (K <= 12): eigenvalues on the
+// diagonal of a, eigenvectors in the columns of e.
+template <int K>
+__device__ void jacobi_small(double (&a)[K][K], double (&e)[K][K]) {
+  for (int r = 0; r < K; ++r)
+    for (int c = 0; c < K; ++c) e[r][c] = r == c ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int r = 0; r < K; ++r)
+      for (int c = 0; c < K; ++c) (r == c ? dg : off) += a[r][c] * a[r][c];
+    if (!(off > 1e-33 * dg)) break;
+    for (int p = 0; p < K - 1; ++p)
+      for (int q = p + 1; q < K; ++q) {
+        const double apq = a[p][q];
+        if (apq == 0.0) continue;
+        const double tau = (a[q][q] - a[p][p]) / (2.0 * apq);
+        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+        for (int r = 0; r < K; ++r) {
+          const double gp = a[r][p], gq = a[r][q];
+          a[r][p] = c * gp - s * gq;
+          a[r][q] = s * gp + c * gq;
+          const double vp = e[r][p], vq = e[r][q];
+          e[r][p] = c * vp - s * vq;
+          e[r][q] = s * vp + c * vq;
+        }
+        for (int r = 0; r < K; ++r) {
+          const double gp = a[p][r], gq = a[q][r];
+          a[p][r] = c * gp - s * gq;
+          a[q][r] = s * gp + c * gq;
+        }
+      }
+  }
+}
+
+// One block.  T = U4^T G U4 (4 x 4).  mode 0 (dual method): T = L L^T, small[0..15] = L^-1 (lower).
+// mode 1 (factorisation): T = Z Lambda Z^T with descending eigenvalues, U4 <- U4 Z (the four leading
+// left singular vectors of W), small[16..19] = singular values sqrt(Lambda).
+__global__ void __launch_bounds__(256)
+dual_small_kernel(int n, const double* __restrict__ G, double* __restrict__ U4, double* __restrict__ small,
+                  int mode) {
+  extern __shared__ double sh[];  // GU [n][4]
+  __shared__ double T[16], Zs[16];
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  for (int w = tid; w < 4 * n; w += nt) {
+    const int a = w >> 2, k = w & 3;
+    const double* g = G + (size_t)a * n;
+    double acc = 0.0;
+    for (int b = 0; b < n; ++b) acc = fma(g[b], U4[4 * b + k], acc);
+    sh[w] = acc;
+  }
+  __syncthreads();
+  for (int pr = warp; pr < 16; pr += nw) {
+    const int k = pr >> 2, l = pr & 3;
+    double acc = 0.0;
+    for (int a = lane; a < n; a += 32) acc += U4[4 * a + k] * sh[4 * a + l];
+    acc = warp_sum(acc);
+    if (lane == 0) T[pr] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double t[4][4];
+    for (int r = 0; r < 4; ++r)
+      for (int c = 0; c < 4; ++c) t[r][c] = 0.5 * (T[4 * r + c] + T[4 * c + r]);
+    if (mode == 0) {
+      double L[4][4] = {}, I[4][4] = {};
+      for (int c = 0; c < 4; ++c)
+        for (int r = c; r < 4; ++r) {
+          double v = t[r][c];
+          for (int m = 0; m < c; ++m) v -= L[r][m] * L[c][m];
+          L[r][c] = r == c ? sqrt(v) : v / L[c][c];
+        }
+      for (int c = 0; c < 4; ++c) {  // lower-triangular inverse by forward substitution
+        I[c][c] = 1.0 / L[c][c];
+        for (int r = c + 1; r < 4; ++r) {
+          double v = 0.0;
+          for (int m = c; m < r; ++m) v -= L[r][m] * I[m][c];
+          I[r][c] = v / L[r][r];
+        }
+      }
+      for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) small[4 * r + c] = I[r][c];
+    } else {
+      double e[4][4];
+      jacobi_small<4>(t, e);
+      int order[4] = {0, 1, 2, 3};
+      for (int a = 0; a < 3; ++a)
+        for (int b = a + 1; b < 4; ++b)
+          if (t[order[b]][order[b]] > t[order[a]][order[a]]) { const int x = order[a]; order[a] = order[b]; order[b] = x; }
+      for (int k = 0; k < 4; ++k) {
+        small[16 + k] = sqrt(t[order[k]][order[k]]);
+        for (int r = 0; r < 4; ++r) Zs[4 * r + k] = e[r][order[k]];
+      }
+    }
+  }
+  __syncthreads();
+  if (mode == 1)
+    for (int a = tid; a < n; a += nt) {
+      const double u0 = U4[4 * a], u1 = U4[4 * a + 1], u2 = U4[4 * a + 2], u3 = U4[4 * a + 3];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) U4[4 * a + k] = u0 * Zs[k] + u1 * Zs[4 + k] + u2 * Zs[8 + k] + u3 * Zs[12 + k];
+    }
+}
+
+// warp per point: c = U4^T wn_j; v_j = L^-1 c -> V4[j][4]; reprojection error of this pass (:219-221)
+__global__ void __launch_bounds__(256)
+dual_v_kernel(int64_t N, int M, int ld, const double* __restrict__ x, const double* __restrict__ Wn,
+              const double* __restrict__ U4, const double* __restrict__ small, double* __restrict__ V4,
+              double* __restrict__ err_part) {
+  extern __shared__ double su[];  // U4 [3M][4]
+  __shared__ double scratch[32];
+  for (int k = threadIdx.x; k < 12 * M; k += blockDim.x) su[k] = U4[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = warps_total();
+  double err = 0.0;
+  for (int64_t j = warp_global(); j < N; j += nw) {
+    const double* xj = x + (size_t)j * M * 3;
+    double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int a = lane; a < 3 * M; a += 32) {
+      const double w = Wn[(size_t)j * ld + a];
+      c0 += w * su[4 * a]; c1 += w * su[4 * a + 1]; c2 += w * su[4 * a + 2]; c3 += w * su[4 * a + 3];
+    }
+    c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); c3 = warp_sum(c3);
+    if (lane == 0) {
+      double* v = V4 + 4 * (size_t)j;
+      v[0] = small[0] * c0;
+      v[1] = small[4] * c0 + small[5] * c1;
+      v[2] = small[8] * c0 + small[9] * c1 + small[10] * c2;
+      v[3] = small[12] * c0 + small[13] * c1 + small[14] * c2 + small[15] * c3;
+    }
+    for (int i = lane; i < M; i += 32) {
+      const double x0 = xj[3 * i], x1 = xj[3 * i + 1], x2 = xj[3 * i + 2];
+      const double* u = su + 12 * i;
+      const double p0 = u[0] * c0 + u[1] * c1 + u[2] * c2 + u[3] * c3;
+      const double p1 = u[4] * c0 + u[5] * c1 + u[6] * c2 + u[7] * c3;
+      const double p2 = u[8] * c0 + u[9] * c1 + u[10] * c2 + u[11] * c3;
+      const double d0 = x0 - p0 / p2, d1 = x1 - p1 / p2, d2 = x2 - p2 / p2;
+      err += d0 * d0 + d1 * d1 + d2 * d2;
+    }
+  }
+  const double tot = block_sum(err, scratch);
+  if (threadIdx.x == 0) err_part[blockIdx.x] = tot;
+}
+
+// per image and warp: sum_j p_j[a] q_ij[b], p = unique entries of v v^T (10), q = of xhat xhat^T (6)
+__global__ void __launch_bounds__(256)
+dual_outer_kernel(int64_t N, int M, const double* __restrict__ x, const double* __restrict__ V4,
+                  double* __restrict__ part /* [warps][M][60] */) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = warp_global(), nw = warps_total();
+  for (int s = 0; s * 32 < M; ++s) {
+    const int i = lane + 32 * s;
+    double acc[60];
+#pragma unroll
+    for (int k = 0; k < 60; ++k) acc[k] = 0.0;
+    for (int64_t j = w; j < N; j += nw) {
+      const double4 v = *reinterpret_cast<const double4*>(V4 + 4 * (size_t)j);
+      double q[6] = {0, 0, 0, 0, 0, 0};
+      if (i < M) {
+        const double* xv = x + ((size_t)j * M + i) * 3;
+        const double x0 = xv[0], x1 = xv[1], x2 = xv[2];
+        const double inv2 = 1.0 / (x0 * x0 + x1 * x1 + x2 * x2);
+        q[0] = x0 * x0 * inv2; q[1] = x0 * x1 * inv2; q[2] = x0 * x2 * inv2;
+        q[3] = x1 * x1 * inv2; q[4] = x1 * x2 * inv2; q[5] = x2 * x2 * inv2;
+      }
+      const double p[10] = {v.x * v.x, v.x * v.y, v.x * v.z, v.x * v.w, v.y * v.y,
+                            v.y * v.z, v.y * v.w, v.z * v.z, v.z * v.w, v.w * v.w};
+#pragma unroll
+      for (int a = 0; a < 10; ++a)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) acc[6 * a + b] = fma(p[a], q[b], acc[6 * a + b]);
+    }
+    if (i < M) {
+      double* out = part + ((size_t)w * M + i) * 60;
+#pragma unroll
+      for (int k = 0; k < 60; ++k) out[k] = acc[k];
+    }
+  }
+}
+
+__device__ __forceinline__ int sym_pair(int a, int b, int n) {  // index of (a, b), a <= b, row-major upper
+  if (a > b) { const int t = a; a = b; b = t; }
+  return a * n - a * (a - 1) / 2 + (b - a);
+}
+
+// thread per image: 12 x 12 matrix from the 10 x 6 products, leading eigenvector -> W12[i][12]
+__global__ void dual_eig12_kernel(int M, const double* __restrict__ R60, double* __restrict__ W12) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const double* r = R60 + (size_t)i * 60;
+  double a[12][12], e[12][12];
+  for (int a0 = 0; a0 < 4; ++a0)
+    for (int b0 = 0; b0 < 3; ++b0)
+      for (int a1 = 0; a1 < 4; ++a1)
+        for (int b1 = 0; b1 < 3; ++b1)
+          a[3 * a0 + b0][3 * a1 + b1] = r[6 * sym_pair(a0, a1, 4) + sym_pair(b0, b1, 3)];
+  jacobi_small<12>(a, e);
+  int best = 0;
+  for (int k = 1; k < 12; ++k)
+    if (a[k][k] > a[best][best]) best = k;
+  for (int k = 0; k < 12; ++k) W12[(size_t)i * 12 + k] = e[k][best];
+}
+
+// e_ij into ebuf[j][i]; per warp and image: sum e^2, sum e -> part[w][2][M]
+__global__ void __launch_bounds__(256)
+dual_e_kernel(int64_t N, int M, const double* __restrict__ x, const double* __restrict__ V4,
+              const double* __restrict__ W12, double* __restrict__ ebuf, double* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = warp_global(), nw = warps_total();
+  for (int s = 0; s * 32 < M; ++s) {
+    const int i = lane + 32 * s;
+    double wv[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) wv[k] = i < M ? W12[(size_t)i * 12 + k] : 0.0;
+    double s2 = 0.0, s1 = 0.0;
+    for (int64_t j = w; j < N; j += nw) {
+      if (i >= M) continue;
+      const double4 v = *reinterpret_cast<const double4*>(V4 + 4 * (size_t)j);
+      const double* xv = x + ((size_t)j * M + i) * 3;
+      const double x0 = xv[0], x1 = xv[1], x2 = xv[2];
+      const double inv = 1.0 / sqrt(x0 * x0 + x1 * x1 + x2 * x2);
+      const double h0 = x0 * inv, h1 = x1 * inv, h2 = x2 * inv;
+      const double e = v.x * (h0 * wv[0] + h1 * wv[1] + h2 * wv[2]) + v.y * (h0 * wv[3] + h1 * wv[4] + h2 * wv[5]) +
+                       v.z * (h0 * wv[6] + h1 * wv[7] + h2 * wv[8]) + v.w * (h0 * wv[9] + h1 * wv[10] + h2 * wv[11]);
+      ebuf[(size_t)j * M + i] = e;
+      s2 += e * e;
+      s1 += e;
+    }
+    if (i < M) {
+      part[((size_t)w * 2) * M + i] = s2;
+      part[((size_t)w * 2 + 1) * M + i] = s1;
+    }
+  }
+}
+
+// sums[0][i] = sum e^2, sums[1][i] = sum e  ->  z
+__global__ void __launch_bounds__(256)
+dual_z_kernel(int64_t N, int M, const double* __restrict__ x, const double* __restrict__ ebuf,
+              const double* __restrict__ sums, double* __restrict__ z) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = warps_total();
+  double scale[kMaxImageSlots];
+#pragma unroll
+  for (int s = 0; s < kMaxImageSlots; ++s) {
+    const int i = lane + 32 * s;
+    scale[s] = i < M ? (sums[M + i] < 0.0 ? -1.0 : 1.0) / sqrt(sums[i]) : 0.0;
+  }
+  for (int64_t j = warp_global(); j < N; j += nw) {
+    double xi[kMaxImageSlots], row = 0.0;
+#pragma unroll
+    for (int s = 0; s < kMaxImageSlots; ++s) {
+      const int i = lane + 32 * s;
+      xi[s] = i < M ? ebuf[(size_t)j * M + i] * scale[s] : 0.0;
+      row += xi[s];
+    }
+    row = warp_sum(row);
+    const double flip = row < 0.0 ? -1.0 : 1.0;  // :212-215
+#pragma unroll
+    for (int s = 0; s < kMaxImageSlots; ++s) {
+      const int i = lane + 32 * s;
+      if (i < M) {
+        const double* xv = x + ((size_t)j * M + i) * 3;
+        z[(size_t)j * M + i] = flip * xi[s] / sqrt(xv[0] * xv[0] + xv[1] * xv[1] + xv[2] * xv[2]);  // :218
+      }
+    }
+  }
+}
+
+// S[k][j] = sum_a U[a][k] W[j][a]  (= diag(Sigma) V^T of the rank-4 factorisation)
+__global__ void __launch_bounds__(256)
+factor_shape_kernel(int64_t N, int n, int ld, const double* __restrict__ Wk, const double* __restrict__ U4,
+                    double* __restrict__ S) {
+  extern __shared__ double su[];
+  for (int k = threadIdx.x; k < 4 * n; k += blockDim.x) su[k] = U4[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = warps_total();
+  for (int64_t j = warp_global(); j < N; j += nw) {
+    double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int a = lane; a < n; a += 32) {
+      const double w = Wk[(size_t)j * ld + a];
+      c0 += w * su[4 * a]; c1 += w * su[4 * a + 1]; c2 += w * su[4 * a + 2]; c3 += w * su[4 * a + 3];
+    }
+    c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2); c3 = warp_sum(c3);
+    if (lane == 0) {
+      S[j] = c0; S[(size_t)N + j] = c1; S[2 * (size_t)N + j] = c2; S[3 * (size_t)N + j] = c3;
+    }
+  }
+}
+
+// Device buffers of one call, freed together on every exit path.
+struct DevBufs {
+  cudaStream_t s;
+  std::vector<void*> ptrs;
+  explicit DevBufs(cudaStream_t s_) : s(s_) {}
+  template <typename T>
+  int alloc(T** p, size_t n) {
+    *p = nullptr;
+    if (cudaMallocAsync(reinterpret_cast<void**>(p), (n ? n : 1) * sizeof(T), s) != cudaSuccess) {
+      set_error("out of device memory (%zu bytes)", n * sizeof(T));
+      cudaGetLastError();
+      return BA_ERR_CUDA;
+    }
+    ptrs.push_back(*p);
+    return BA_OK;
+  }
+  ~DevBufs() {
+    for (void* p : ptrs) cudaFreeAsync(p, s);
+    cudaStreamSynchronize(s);
+  }
+};
+
+static int leading_subspace(int n, int ld, int64_t k_pad, const GramWorkspace* ws, const double* Wk, double* P,
+                            double* G, double* V, double* U4, double* ev, int* status, bool warm, cudaStream_t s) {
+  static const bool force_jacobi = std::getenv("BA_DEPTH_JACOBI") != nullptr;
+  BA_TRY(gram_launch(ws, Wk, P, s));
+  gram_symmetrize_kernel<<<(n * n + 255) / 256, 256, 0, s>>>(n, ld, P, G);
+  if (!force_jacobi)
+    subspace_eig_kernel<<<1, 256, (size_t)8 * n * sizeof(double), s>>>(n, G, U4, warm ? 1 : 0, 2000, status);
+  const size_t jac_smem = (size_t)(2 * ((n + 1) / 2)) * sizeof(double) + (size_t)2 * (n + 1) * sizeof(int) + 16;
+  // the Jacobi fallback rotates its matrix in place and G is still needed afterwards: it works on
+  // a copy (V is the eigenvector store, the copy lives behind it)
+  BA_CUDA(cudaMemcpyAsync(V + (size_t)n * n, G, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  jacobi_eig_kernel<<<1, 256, jac_smem, s>>>(n, V + (size_t)n * n, V, U4, ev, force_jacobi ? nullptr : status);
+  g_launch_count += 3;
+  (void)k_pad;
+  return BA_OK;
+}
+
 }  // namespace ba
 
 using namespace ba;
+
+extern "C" int ba_projective_depth_dual(int device, int64_t n_points, int32_t n_images, const double* x, double f0,
+                                        double tolerance, int max_iter, double* z, double* errors, int* n_iter,
+                                        int mem, void* stream) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: the projective-depth iteration has no CPU path");
+    return BA_ERR_NO_DEVICE;
+  }
+  if (!x || !z || !n_iter || n_points < 4 || n_images < 2 || n_images > 32 * kMaxImageSlots || device < 0 ||
+      device >= ndev) {
+    set_error("projective depth (dual): need >= 4 points, 2..64 images and valid pointers");
+    return BA_ERR_INVALID;
+  }
+  if (max_iter < 1) max_iter = 1;  // the reference runs at least one pass (:162-231)
+  cudaStream_t s = (cudaStream_t)stream;
+  BA_CUDA(cudaSetDevice(device));
+  int num_sms = 148;
+  BA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+  const int64_t N = n_points;
+  const int M = n_images, n = 3 * M;
+  const int ld = (n + 7) / 8 * 8;
+  const int64_t k_pad = (N + 31) / 32 * 32;
+  const size_t d = sizeof(double);
+  const int grid = balanced_blocks((N + 7) / 8, (int64_t)num_sms * 8);
+  const int64_t nwarps = (int64_t)grid * 8;
+  DevBufs bufs(s);
+  double *dx = nullptr, *dz = nullptr, *Wn = nullptr, *P = nullptr, *G = nullptr, *V = nullptr, *U4 = nullptr,
+         *ev = nullptr, *part = nullptr, *sums = nullptr, *small = nullptr, *V4 = nullptr, *R60 = nullptr,
+         *W12 = nullptr, *ebuf = nullptr, *errp = nullptr, *dE = nullptr;
+  int* status = nullptr;
+  BA_TRY(bufs.alloc(&Wn, (size_t)k_pad * ld));
+  BA_TRY(bufs.alloc(&P, (size_t)ld * ld));
+  BA_TRY(bufs.alloc(&G, (size_t)n * n));
+  BA_TRY(bufs.alloc(&V, (size_t)2 * n * n));
+  BA_TRY(bufs.alloc(&U4, (size_t)4 * n));
+  BA_TRY(bufs.alloc(&ev, 4));
+  BA_TRY(bufs.alloc(&part, (size_t)nwarps * M * 60));
+  BA_TRY(bufs.alloc(&sums, (size_t)2 * M));
+  BA_TRY(bufs.alloc(&small, 32));
+  BA_TRY(bufs.alloc(&V4, (size_t)4 * N));
+  BA_TRY(bufs.alloc(&R60, (size_t)60 * M));
+  BA_TRY(bufs.alloc(&W12, (size_t)12 * M));
+  BA_TRY(bufs.alloc(&ebuf, (size_t)N * M));
+  BA_TRY(bufs.alloc(&errp, (size_t)grid));
+  BA_TRY(bufs.alloc(&dE, 1));
+  BA_TRY(bufs.alloc(&status, 1));
+  if (mem == BA_MEM_DEVICE) {
+    dx = const_cast<double*>(x);
+    dz = z;
+  } else {
+    BA_TRY(bufs.alloc(&dx, (size_t)N * M * 3));
+    BA_TRY(bufs.alloc(&dz, (size_t)N * M));
+    BA_CUDA(cudaMemcpyAsync(dx, x, (size_t)N * M * 3 * d, cudaMemcpyHostToDevice, s));
+  }
+  BA_CUDA(cudaMemsetAsync(Wn, 0, (size_t)k_pad * ld * d, s));
+  BA_CUDA(cudaMemsetAsync(P, 0, (size_t)ld * ld * d, s));
+  BA_CUDA(cudaMemsetAsync(status, 0, sizeof(int), s));
+  {
+    std::vector<double> ones((size_t)N * M, 1.0);  // :160  z = 1
+    BA_CUDA(cudaMemcpyAsync(dz, ones.data(), ones.size() * d, cudaMemcpyHostToDevice, s));
+    BA_CUDA(cudaStreamSynchronize(s));
+  }
+  GramWorkspace ws;
+  int st = gram_prepare(&ws, ld, k_pad, num_sms, s);
+  int it = 0;
+  double E = 0.0;
+  while (st == BA_OK) {
+    dual_norm_kernel<<<grid, 256, 0, s>>>(N, M, dx, dz, part);
+    colsum_finish_kernel<<<(M + 63) / 64, 64, 0, s>>>(part, nwarps, M, sums);
+    dual_scale_kernel<<<grid, 256, 0, s>>>(N, M, ld, dx, dz, sums, Wn);
+    // the Jacobi fallback needs its own copy of G (see leading_subspace)
+    st = leading_subspace(n, ld, k_pad, &ws, Wn, P, G, V, U4, ev, status, it > 0, s);
+    if (st != BA_OK) break;
+    dual_small_kernel<<<1, 256, (size_t)4 * n * d, s>>>(n, G, U4, small, 0);
+    dual_v_kernel<<<grid, 256, (size_t)12 * M * d, s>>>(N, M, ld, dx, Wn, U4, small, V4, errp);
+    depth_error_kernel<<<1, 256, 0, s>>>(errp, grid, (double)N * (double)M, f0, dE);
+    dual_outer_kernel<<<grid, 256, 0, s>>>(N, M, dx, V4, part);
+    colsum_finish_kernel<<<(60 * M + 127) / 128, 128, 0, s>>>(part, nwarps, 60 * M, R60);
+    dual_eig12_kernel<<<(M + 31) / 32, 32, 0, s>>>(M, R60, W12);
+    dual_e_kernel<<<grid, 256, 0, s>>>(N, M, dx, V4, W12, ebuf, part);
+    colsum_finish_kernel<<<(2 * M + 63) / 64, 64, 0, s>>>(part, nwarps, 2 * M, sums);
+    dual_z_kernel<<<grid, 256, 0, s>>>(N, M, dx, ebuf, sums, dz);
+    g_launch_count += 12;
+    if (cudaMemcpyAsync(&E, dE, d, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+      set_error("projective depth (dual): %s", cudaGetErrorString(cudaGetLastError()));
+      st = BA_ERR_CUDA;
+      break;
+    }
+    if (errors) errors[it] = E;
+    ++it;
+    if (E < tolerance || it >= max_iter) break;  // :228-229
+  }
+  *n_iter = it;
+  if (st == BA_OK && mem != BA_MEM_DEVICE &&
+      cudaMemcpyAsync(z, dz, (size_t)N * M * d, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    st = BA_ERR_CUDA;
+  gram_release(&ws, s);
+  return st;  // ~DevBufs frees everything and synchronises the stream
+}
+
+extern "C" int ba_factorize_rank4(int device, int64_t n_cols, int32_t n_rows, const double* Wt, double* M_out,
+                                  double* S_out, double* sigma_out, int mem, void* stream) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: the factorisation has no CPU path");
+    return BA_ERR_NO_DEVICE;
+  }
+  if (!Wt || !M_out || !S_out || n_cols < 4 || n_rows < 4 || n_rows > 192 || device < 0 || device >= ndev) {
+    set_error("factorisation: need >= 4 columns, 4..192 rows and valid pointers");
+    return BA_ERR_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  BA_CUDA(cudaSetDevice(device));
+  int num_sms = 148;
+  BA_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+  const int64_t N = n_cols;
+  const int n = n_rows;
+  const int ld = (n + 7) / 8 * 8;
+  const int64_t k_pad = (N + 31) / 32 * 32;
+  const size_t d = sizeof(double);
+  const int grid = balanced_blocks((N + 7) / 8, (int64_t)num_sms * 8);
+  DevBufs bufs(s);
+  double *dW = nullptr, *Wk = nullptr, *P = nullptr, *G = nullptr, *V = nullptr, *U4 = nullptr, *ev = nullptr,
+         *small = nullptr, *dS = nullptr;
+  int* status = nullptr;
+  BA_TRY(bufs.alloc(&Wk, (size_t)k_pad * ld));
+  BA_TRY(bufs.alloc(&P, (size_t)ld * ld));
+  BA_TRY(bufs.alloc(&G, (size_t)n * n));
+  BA_TRY(bufs.alloc(&V, (size_t)2 * n * n));
+  BA_TRY(bufs.alloc(&U4, (size_t)4 * n));
+  BA_TRY(bufs.alloc(&ev, 4));
+  BA_TRY(bufs.alloc(&small, 32));
+  BA_TRY(bufs.alloc(&status, 1));
+  if (mem == BA_MEM_DEVICE) {
+    dW = const_cast<double*>(Wt);
+    dS = S_out;
+  } else {
+    BA_TRY(bufs.alloc(&dW, (size_t)N * n));
+    BA_TRY(bufs.alloc(&dS, (size_t)4 * N));
+    BA_CUDA(cudaMemcpyAsync(dW, Wt, (size_t)N * n * d, cudaMemcpyHostToDevice, s));
+  }
+  BA_CUDA(cudaMemsetAsync(Wk, 0, (size_t)k_pad * ld * d, s));
+  BA_CUDA(cudaMemsetAsync(P, 0, (size_t)ld * ld * d, s));
+  BA_CUDA(cudaMemsetAsync(status, 0, sizeof(int), s));
+  pad_rows_kernel<<<grid, 256, 0, s>>>(N, n, ld, dW, Wk);
+  GramWorkspace ws;
+  int st = gram_prepare(&ws, ld, k_pad, num_sms, s);
+  if (st == BA_OK) st = leading_subspace(n, ld, k_pad, &ws, Wk, P, G, V, U4, ev, status, false, s);
+  if (st == BA_OK) {
+    dual_small_kernel<<<1, 256, (size_t)4 * n * d, s>>>(n, G, U4, small, 1);
+    factor_shape_kernel<<<grid, 256, (size_t)4 * n * d, s>>>(N, n, ld, Wk, U4, dS);
+    g_launch_count += 3;
+    const cudaMemcpyKind kind = mem == BA_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (cudaMemcpyAsync(M_out, U4, (size_t)4 * n * d, kind, s) != cudaSuccess ||
+        (sigma_out && cudaMemcpyAsync(sigma_out, small + 16, 4 * d, kind, s) != cudaSuccess) ||
+        (mem != BA_MEM_DEVICE && cudaMemcpyAsync(S_out, dS, (size_t)4 * N * d, cudaMemcpyDeviceToHost, s) != cudaSuccess) ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+      set_error("factorisation: %s", cudaGetErrorString(cudaGetLastError()));
+      st = BA_ERR_CUDA;
+    }
+  }
+  gram_release(&ws, s);
+  return st;
+}
 
 extern "C" int ba_projective_depth_primary(int device, int64_t n_points, int32_t n_images, const double* x,
                                            double f0, double tolerance, int max_iter, double* z,

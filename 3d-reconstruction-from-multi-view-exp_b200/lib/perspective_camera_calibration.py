@@ -1,9 +1,20 @@
 """Shadow module for the reference's ``lib/perspective_camera_calibration.py``: everything is the
 reference's own code (loaded from the next ``lib/perspective_camera_calibration.py`` on
-``sys.path``) except ``_compute_projective_depth_primary_method`` (``:61-144``), which runs on the
-GPU.  The replacement is installed in the reference module's own namespace, so that its
-``perspective_self_calibration(..., method="primary")`` (``:513-540``) picks it up.  Only meaningful
-when the reference checkout follows this package's directory on ``sys.path``."""
+``sys.path``) except the heavy stages of ``perspective_self_calibration`` (``:513-540``), which run
+on the GPU:
+
+  * ``_compute_projective_depth_primary_method`` (``:61-144``) and
+    ``_compute_projective_depth_dual_method`` (``:147-235`` -- the script's choice, an
+    (n_images, n_points, n_points) array in the reference, O(n_images x n_points) here);
+  * ``factorization_method`` (``lib/factorization.py:5-15``, a full SVD with an n_points x n_points
+    factor in the reference) for the rank-4 case.
+
+The O(n_images) Euclidean upgrade (``:238-411``) and the O(n_points) NumPy lines of
+``_reconstruct_3d`` / ``correct_world_coordinates`` stay the reference's own code.  The replacements
+are installed in the reference module's own namespace, so that its ``perspective_self_calibration``
+picks them up.  Inputs the kernels do not take (more than 64 images, fewer than 4 points, another
+rank) go to the reference's implementation.  Only meaningful when the reference checkout follows
+this package's directory on ``sys.path``."""
 import importlib
 import importlib.util
 import os
@@ -30,8 +41,37 @@ def _load_reference_module():
 
 
 _ref = _load_reference_module()
-_ref._compute_projective_depth_primary_method = importlib.import_module(
-    os.path.basename(_PKG_DIR) + ".projective_depth").compute_projective_depth_primary_method
+_gpu = importlib.import_module(os.path.basename(_PKG_DIR) + ".projective_depth")
+_ref_primary = _ref._compute_projective_depth_primary_method
+_ref_dual = _ref._compute_projective_depth_dual_method
+_ref_factorization = _ref.factorization_method
+
+
+def _fits(x):
+    return x.ndim == 3 and x.shape[0] >= 4 and 2 <= x.shape[1] <= _gpu.MAX_IMAGES
+
+
+def _primary(x, f0, tolerance, max_iter=200):
+    if not _fits(x):
+        return _ref_primary(x, f0, tolerance, max_iter)
+    return _gpu.compute_projective_depth_primary_method(x, f0, tolerance, max(int(max_iter), 1))
+
+
+def _dual(x, f0, tolerance, max_iter=50):
+    if not _fits(x):
+        return _ref_dual(x, f0, tolerance, max_iter)
+    return _gpu.compute_projective_depth_dual_method(x, f0, tolerance, max_iter)
+
+
+def _factorization(W, n_rank=4):
+    if n_rank != 4 or W.ndim != 2 or not (4 <= W.shape[0] <= 3 * _gpu.MAX_IMAGES) or W.shape[1] < 4:
+        return _ref_factorization(W, n_rank)
+    return _gpu.factorization_method(W, n_rank)
+
+
+_ref._compute_projective_depth_primary_method = _primary
+_ref._compute_projective_depth_dual_method = _dual
+_ref.factorization_method = _factorization
 for _name in dir(_ref):
     if not _name.startswith("__"):
         globals()[_name] = getattr(_ref, _name)

@@ -276,6 +276,29 @@ int ba_projective_depth_primary(int device, int64_t n_points, int32_t n_images, 
                                 double tolerance, int max_iter, double* z, double* errors, int* n_iter,
                                 int mem, void* stream);
 
+/* _compute_projective_depth_dual_method (reference lib/perspective_camera_calibration.py:147-235) --
+ * the method euclidiean_reconstruction.py:42 selects.  Same arguments as the primary entry point.
+ * The reference builds an (n_images, n_points, n_points) array (:188); here every per-image N x N
+ * eigenproblem is reduced to a 12 x 12 one (csrc/k7_projective_depth.cu), memory is O(n_images x
+ * n_points).  The sign of each image's column of z -- which the reference leaves to LAPACK's
+ * eigenvector convention (:206-215) -- is fixed by making the column's unit eigenvector sum
+ * non-negative before the reference's row rule is applied; the Euclidean upgrade does not depend on
+ * it.  max_iter < 1 runs one pass, like the reference.  2 <= n_images <= 64. */
+int ba_projective_depth_dual(int device, int64_t n_points, int32_t n_images, const double* x, double f0,
+                             double tolerance, int max_iter, double* z, double* errors, int* n_iter,
+                             int mem, void* stream);
+
+/* factorization_method(W, n_rank=4) (reference lib/factorization.py:5-15), the step between the
+ * projective depths and the Euclidean upgrade (lib/perspective_camera_calibration.py:533): rank-4
+ * truncated SVD W ~ M S of the (n_rows x n_cols) matrix, n_rows = 3 n_images <= 192.  Wt is W
+ * TRANSPOSED, [n_cols][n_rows] row-major (what the reference's `W.reshape(N, -1).T` is a view of);
+ * M_out[n_rows][4] = the four leading left singular vectors, S_out[4][n_cols] = diag(Sigma) V^T,
+ * sigma_out[4] (may be NULL) the singular values.  The reference's full SVD allocates an
+ * n_cols x n_cols factor; here the Gram matrix W W^T goes through the FP64 tensor cores and only its
+ * leading eigenspace is computed.  Singular vectors are defined up to sign, as in LAPACK. */
+int ba_factorize_rank4(int device, int64_t n_cols, int32_t n_rows, const double* Wt, double* M_out,
+                       double* S_out, double* sigma_out, int mem, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
