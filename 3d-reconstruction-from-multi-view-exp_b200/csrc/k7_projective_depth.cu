@@ -454,7 +454,7 @@ __global__ void depth_error_kernel(const double* __restrict__ part, int n, doubl
 //   dual_small_kernel      T = U4^T G U4, Cholesky, L^-1
 //   dual_v_kernel          warp per point: c = U4^T wn_j, v_j = L^-1 c, reprojection-error share
 //   dual_outer_kernel      per image sum_j (v v^T) (x) (xhat xhat^T): 10 x 6 unique products
-//   dual_eig12_kernel      thread per image: cyclic Jacobi on the 12 x 12 matrix, leading eigenvector
+//   dual_eig12_kernel      warp per image: cyclic Jacobi on the 12 x 12 matrix in shared memory
 //   dual_e_kernel          e_ij = sum v_j[a] xhat_ij[b] w_i[a, b]; per-image sum e^2, sum e
 //   dual_z_kernel          xi = e / |e_i| with each image's sum made non-negative (the sign LAPACK
 //                          leaves open, see oracle/depth_oracle.py), then the reference's row rule
@@ -531,8 +531,11 @@ __device__ void jacobi_small(double (&a)[K][K], double (&e)[K][K]) {
   for (int sweep = 0; sweep < 30; ++sweep) {
     double off = 0.0, dg = 0.0;
     for (int r = 0; r < K; ++r)
-      for (int c = 0; c < K; ++c) (r == c ? dg : off) += a[r][c] * a[r][c];
-    if (!(off > 1e-33 * dg)) break;
+      for (int c = 0; c < K; ++c) {
+        const double v = a[r][c] * a[r][c];
+        if (r == c) dg += v; else off += v;
+      }
+    if (!(off > 1e-30 * dg)) break;
     for (int p = 0; p < K - 1; ++p)
       for (int q = p + 1; q < K; ++q) {
         const double apq = a[p][q];
@@ -708,22 +711,72 @@ __device__ __forceinline__ int sym_pair(int a, int b, int n) {  // index of (a, 
   return a * n - a * (a - 1) / 2 + (b - a);
 }
 
-// thread per image: 12 x 12 matrix from the 10 x 6 products, leading eigenvector -> W12[i][12]
-__global__ void dual_eig12_kernel(int M, const double* __restrict__ R60, double* __restrict__ W12) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// Cyclic Jacobi on a symmetric K x K matrix by ONE WARP: A and the eigenvector matrix E live in
+// shared memory, lane r owns row r of the column rotation and column r of the row rotation.
+// (A single-thread version on local-memory arrays -- the straightforward code, fine on the host -- is
+// miscompiled by nvcc 12.9 for sm_100a at K = 12: it stops converging after the first sweep;
+// tools/gpu/jac_test.cu reproduces it next to this version.)  Returns with the eigenvalues on the
+// diagonal of a; fixed order of operations.
+template <int K>
+__device__ void jacobi_warp(double* a, double* e) {
+  const int lane = threadIdx.x & 31;
+  for (int k = lane; k < K * K; k += 32) e[k] = (k / K == k % K) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int k = lane; k < K * K; k += 32) {
+      const double v = a[k] * a[k];
+      if (k / K == k % K) dg += v; else off += v;
+    }
+    off = warp_sum(off);
+    dg = warp_sum(dg);
+    if (!(off > 1e-30 * dg)) break;
+    for (int p = 0; p < K - 1; ++p)
+      for (int q = p + 1; q < K; ++q) {
+        const double apq = a[p * K + q];
+        double c = 1.0, s = 0.0;
+        if (apq != 0.0) {
+          const double tau = (a[q * K + q] - a[p * K + p]) / (2.0 * apq);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + t * t);
+          s = t * c;
+        }
+        __syncwarp();
+        if (lane < K) {  // columns p, q of A and E
+          const double gp = a[lane * K + p], gq = a[lane * K + q];
+          a[lane * K + p] = c * gp - s * gq;
+          a[lane * K + q] = s * gp + c * gq;
+          const double vp = e[lane * K + p], vq = e[lane * K + q];
+          e[lane * K + p] = c * vp - s * vq;
+          e[lane * K + q] = s * vp + c * vq;
+        }
+        __syncwarp();
+        if (lane < K) {  // rows p, q of A
+          const double gp = a[p * K + lane], gq = a[q * K + lane];
+          a[p * K + lane] = c * gp - s * gq;
+          a[q * K + lane] = s * gp + c * gq;
+        }
+        __syncwarp();
+      }
+  }
+}
+
+// warp (= block) per image: 12 x 12 matrix from the 10 x 6 products, leading eigenvector -> W12[i][12]
+__global__ void __launch_bounds__(32) dual_eig12_kernel(int M, const double* __restrict__ R60, double* __restrict__ W12) {
+  __shared__ double a[144], e[144];
+  const int i = blockIdx.x, lane = threadIdx.x;
   if (i >= M) return;
   const double* r = R60 + (size_t)i * 60;
-  double a[12][12], e[12][12];
-  for (int a0 = 0; a0 < 4; ++a0)
-    for (int b0 = 0; b0 < 3; ++b0)
-      for (int a1 = 0; a1 < 4; ++a1)
-        for (int b1 = 0; b1 < 3; ++b1)
-          a[3 * a0 + b0][3 * a1 + b1] = r[6 * sym_pair(a0, a1, 4) + sym_pair(b0, b1, 3)];
-  jacobi_small<12>(a, e);
+  for (int k = lane; k < 144; k += 32) {
+    const int row = k / 12, col = k - 12 * row;
+    a[k] = r[6 * sym_pair(row / 3, col / 3, 4) + sym_pair(row % 3, col % 3, 3)];
+  }
+  __syncwarp();
+  jacobi_warp<12>(a, e);
   int best = 0;
   for (int k = 1; k < 12; ++k)
-    if (a[k][k] > a[best][best]) best = k;
-  for (int k = 0; k < 12; ++k) W12[(size_t)i * 12 + k] = e[k][best];
+    if (a[k * 12 + k] > a[best * 12 + best]) best = k;
+  if (lane < 12) W12[(size_t)i * 12 + lane] = e[lane * 12 + best];
 }
 
 // e_ij into ebuf[j][i]; per warp and image: sum e^2, sum e -> part[w][2][M]
@@ -856,6 +909,8 @@ static int leading_subspace(int n, int ld, int64_t k_pad, const GramWorkspace* w
 
 using namespace ba;
 
+static double* const* g_dual_probe = nullptr;
+
 extern "C" int ba_projective_depth_dual(int device, int64_t n_points, int32_t n_images, const double* x, double f0,
                                         double tolerance, int max_iter, double* z, double* errors, int* n_iter,
                                         int mem, void* stream) {
@@ -934,11 +989,16 @@ extern "C" int ba_projective_depth_dual(int device, int64_t n_points, int32_t n_
     depth_error_kernel<<<1, 256, 0, s>>>(errp, grid, (double)N * (double)M, f0, dE);
     dual_outer_kernel<<<grid, 256, 0, s>>>(N, M, dx, V4, part);
     colsum_finish_kernel<<<(60 * M + 127) / 128, 128, 0, s>>>(part, nwarps, 60 * M, R60);
-    dual_eig12_kernel<<<(M + 31) / 32, 32, 0, s>>>(M, R60, W12);
+    dual_eig12_kernel<<<M, 32, 0, s>>>(M, R60, W12);
     dual_e_kernel<<<grid, 256, 0, s>>>(N, M, dx, V4, W12, ebuf, part);
     colsum_finish_kernel<<<(2 * M + 63) / 64, 64, 0, s>>>(part, nwarps, 2 * M, sums);
     dual_z_kernel<<<grid, 256, 0, s>>>(N, M, dx, ebuf, sums, dz);
     g_launch_count += 12;
+    if (cudaGetLastError() != cudaSuccess) {
+      set_error("projective depth (dual): a kernel launch failed");
+      st = BA_ERR_CUDA;
+      break;
+    }
     if (cudaMemcpyAsync(&E, dE, d, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
         cudaStreamSynchronize(s) != cudaSuccess) {
       set_error("projective depth (dual): %s", cudaGetErrorString(cudaGetLastError()));
@@ -953,8 +1013,27 @@ extern "C" int ba_projective_depth_dual(int device, int64_t n_points, int32_t n_
   if (st == BA_OK && mem != BA_MEM_DEVICE &&
       cudaMemcpyAsync(z, dz, (size_t)N * M * d, cudaMemcpyDeviceToHost, s) != cudaSuccess)
     st = BA_ERR_CUDA;
+  if (st == BA_OK && g_dual_probe) {
+    // intermediates of the LAST pass for the tests (host buffers registered by ba_depth_dual_probe)
+    double* const* pr = g_dual_probe;
+    const double* src[6] = {V4, R60, W12, ebuf, sums, U4};
+    const size_t cnt[6] = {(size_t)4 * N, (size_t)60 * M, (size_t)12 * M, (size_t)N * M, (size_t)2 * M, (size_t)4 * n};
+    for (int k = 0; k < 6; ++k)
+      if (pr[k]) cudaMemcpyAsync(pr[k], src[k], cnt[k] * d, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+  }
   gram_release(&ws, s);
   return st;  // ~DevBufs frees everything and synchronises the stream
+}
+
+// Tests only: host buffers that the next ba_projective_depth_dual call fills with the intermediates
+// of its last pass -- V4 [N][4], R60 [M][60], W12 [M][12], e [N][M], sums [2][M], U4 [3M][4]; any may
+// be NULL; pass all NULL to switch the probe off again.
+extern "C" int ba_depth_dual_probe(double* V4, double* R60, double* W12, double* e, double* sums, double* U4) {
+  static double* slots[6];
+  slots[0] = V4; slots[1] = R60; slots[2] = W12; slots[3] = e; slots[4] = sums; slots[5] = U4;
+  g_dual_probe = (V4 || R60 || W12 || e || sums || U4) ? slots : nullptr;
+  return BA_OK;
 }
 
 extern "C" int ba_factorize_rank4(int device, int64_t n_cols, int32_t n_rows, const double* Wt, double* M_out,

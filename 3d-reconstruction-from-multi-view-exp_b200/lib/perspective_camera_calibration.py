@@ -42,9 +42,9 @@ def _load_reference_module():
 
 _ref = _load_reference_module()
 _gpu = importlib.import_module(os.path.basename(_PKG_DIR) + ".projective_depth")
-_ref_primary = _ref._compute_projective_depth_primary_method
-_ref_dual = _ref._compute_projective_depth_dual_method
-_ref_factorization = _ref.factorization_method
+_ref_primary = getattr(_ref, "_compute_projective_depth_primary_method", None)
+_ref_dual = getattr(_ref, "_compute_projective_depth_dual_method", None)
+_ref_factorization = getattr(_ref, "factorization_method", None)
 
 
 def _fits(x):
@@ -69,9 +69,12 @@ def _factorization(W, n_rank=4):
     return _gpu.factorization_method(W, n_rank)
 
 
-_ref._compute_projective_depth_primary_method = _primary
-_ref._compute_projective_depth_dual_method = _dual
-_ref.factorization_method = _factorization
+if _ref_primary is not None:
+    _ref._compute_projective_depth_primary_method = _primary
+if _ref_dual is not None:
+    _ref._compute_projective_depth_dual_method = _dual
+if _ref_factorization is not None:
+    _ref.factorization_method = _factorization
 for _name in dir(_ref):
     if not _name.startswith("__"):
         globals()[_name] = getattr(_ref, _name)
