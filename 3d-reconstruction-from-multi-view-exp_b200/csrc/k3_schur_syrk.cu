@@ -337,13 +337,10 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
   auto empty_bar = [&](int st) { return bars + 8u * (kTmaStages + st); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // diagonal tiles: only the sub-tiles on or below the diagonal, dealt to warps 0..9 (see
-  // syrk_dmma_kernel); the other consumer warps leave at once and are not counted by `empty`
-  const int n_live = diag ? WR * (WR + 1) / 2 : kTmaConsumerWarps;
   if (threadIdx.x == 0) {
     for (int st = 0; st < kTmaStages; ++st) {
       mbar_init(full_bar(st), 1);
-      mbar_init(empty_bar(st), n_live);
+      mbar_init(empty_bar(st), kTmaConsumerWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -370,14 +367,93 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
   }
 
   // ---- consumer warps -----------------------------------------------------------------------------
-  int wr = warp / WC, wc = warp % WC;
-  if (diag) {
-    if (warp >= n_live) return;
-    wr = 0;
-    while ((wr + 1) * (wr + 2) / 2 <= warp) ++wr;
-    wc = warp - wr * (wr + 1) / 2;
-  }
   const int kq = lane & 3;
+  if (diag) {
+    // Diagonal tile: only the 136 fragments (8 x 8) on or below the diagonal of the 16 x 16 fragment
+    // grid are needed.  Fragment rows r and 15 - r together hold 17 of them; the pair is shared by
+    // two warps, one taking nine fragments (row 15 - r, columns 0..8), the other eight (the rest of
+    // row 15 - r and all of row r).  Which warp of a pair takes nine alternates so that every
+    // scheduler partition (warp % 4) carries 34 fragments per k-step: 0.53 of a full tile's 64
+    // instead of the 0.75 of the square sub-tile mapping (3 of 4 rounds).
+    const int pr = warp >> 1;
+    const bool nine = (((warp & 1) ^ ((warp >> 2) & 1)) == 0);
+    const int r_hi = 15 - pr, r_lo = pr;
+    const int n_hi = nine ? 9 : 7 - pr;        // fragments this warp takes from row r_hi
+    const int c_hi0 = nine ? 0 : 9;            // ... starting at this column
+    const int nfr = nine ? 9 : 8;
+    const int frag_rows_valid = (n_valid - ti * TILE + 7) / 8;  // ragged last tile
+    int boffj[9];
+    bool usej[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const bool hi = j < n_hi;
+      const int rf = hi ? r_hi : r_lo;
+      const int cf = hi ? c_hi0 + j : j - n_hi;
+      usej[j] = j < nfr && rf < frag_rows_valid;
+      boffj[j] = (cf * KC + kq) * 8 + (lane >> 2);
+    }
+    const int aoff_hi = (r_hi * KC + kq) * 8 + (lane >> 2);
+    const int aoff_lo = (r_lo * KC + kq) * 8 + (lane >> 2);
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) any |= usej[j];
+    double dacc[9][2];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) dacc[j][0] = dacc[j][1] = 0.0;
+    for (int kc = 0; kc < nk; ++kc) {
+      const int st = kc % kTmaStages;
+      mbar_wait(full_bar(st), (unsigned)(kc / kTmaStages) & 1u);
+      const double* a = stages + (size_t)st * 2 * kTmaOperandDoubles;
+      if (any) {
+#pragma unroll
+        for (int kk = 0; kk < KC; kk += 4) {
+          const double fa_hi = a[aoff_hi + kk * 8], fa_lo = a[aoff_lo + kk * 8];
+          double fb[9];
+#pragma unroll
+          for (int j = 0; j < 9; ++j) fb[j] = a[boffj[j] + kk * 8];
+#pragma unroll
+          for (int j = 0; j < 9; ++j)
+            if (usej[j]) dmma884(dacc[j][0], dacc[j][1], j < n_hi ? fa_hi : fa_lo, fb[j]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(st));
+    }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      if (!usej[j]) continue;
+      const bool hi = j < n_hi;
+      const int rl = 8 * (hi ? r_hi : r_lo) + (lane >> 2);             // row / column inside the tile
+      const int cl = 8 * (hi ? c_hi0 + j : j - n_hi) + 2 * (lane & 3);
+      if (SUB) {
+        const int r = ti * TILE + rl, c = ti * TILE + cl;
+        if (r >= n_store || c > r) continue;
+        const size_t off = (size_t)r * ld + c;
+        double* p = part + off;
+        const bool push = sp.world > 1 && ti * TILE < sp.push_cols;
+        if (c + 1 <= r) {
+          double2 v = *reinterpret_cast<double2*>(p);
+          v.x -= dacc[j][0];
+          v.y -= dacc[j][1];
+          *reinterpret_cast<double2*>(p) = v;
+          if (push)
+            for (int q = 0; q < sp.world; ++q)
+              if (q != sp.rank) *reinterpret_cast<double2*>(sp.peer[q] + off) = v;
+        } else {
+          const double v = *p - dacc[j][0];
+          *p = v;
+          if (push)
+            for (int q = 0; q < sp.world; ++q)
+              if (q != sp.rank) sp.peer[q][off] = v;
+        }
+      } else {
+        *reinterpret_cast<double2*>(part + (size_t)blockIdx.x * TILE * TILE + (size_t)rl * TILE + cl) =
+            make_double2(dacc[j][0], dacc[j][1]);
+      }
+    }
+    return;
+  }
+  const int wr = warp / WC, wc = warp % WC;
   int vm = 0, vn = 0;
 #pragma unroll
   for (int i = 0; i < FM; ++i) vm += (ti * TILE + wr * WM + 8 * i) < n_valid;
@@ -533,7 +609,18 @@ int syrk_feed_is_tma();
 static double tile_weight(int TILE, int WR, int WC, int occ, int ti, int tj, int n_valid, int64_t k_pad = 0) {
   const int WM = TILE / WR, WN = TILE / WC, FM = WM / 8, FN = WN / 8;
   double load[4] = {0, 0, 0, 0};
-  for (int warp = 0; warp < WR * WC; ++warp) {
+  const bool folded_diag = ti == tj && TILE == kTmaTile && occ == 1 && syrk_feed_is_tma();
+  if (folded_diag) {
+    // the TMA kernel's diagonal mapping: fragment rows r and 15 - r shared by two warps (9 + 8)
+    const int rows_valid = std::min(16, (n_valid - ti * TILE + 7) / 8);
+    for (int warp = 0; warp < 16; ++warp) {
+      const int pr = warp >> 1;
+      const bool nine = (((warp & 1) ^ ((warp >> 2) & 1)) == 0);
+      const int r_hi = 15 - pr, r_lo = pr, n_hi = nine ? 9 : 7 - pr, nfr = nine ? 9 : 8;
+      for (int j = 0; j < nfr; ++j) load[warp % 4] += ((j < n_hi ? r_hi : r_lo) < rows_valid) ? 1.0 : 0.0;
+    }
+  }
+  for (int warp = 0; warp < WR * WC && !folded_diag; ++warp) {
     int wr = warp / WC, wc = warp % WC;
     bool live = true;
     if (ti == tj && WR == WC) {
