@@ -456,69 +456,10 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
     }
     return;
   }
-  const int rows_valid = min(kTmaGroups, (n_valid - ti * TILE + 7) / 8);  // valid fragment rows of the tile
-  if (rows_valid < kTmaGroups) {
-    // Thin tile (the ragged last tile row, e.g. 16 of 128 rows at 200 cameras).  With the square
-    // sub-tile mapping only the warps of the first sub-tile row would work -- one warp per scheduler
-    // partition, nothing to overlap its load latency with: such a tile cost 0.34 of a full one for
-    // 0.125 of the work.  Here warp w owns fragment COLUMN w and all valid fragment rows: every warp
-    // has rows_valid DMMAs per k-step, the cost is proportional to the valid rows.
-    const int boffc = (warp * KC + kq) * 8 + (lane >> 2);
-    const int aoffr = kq * 8 + (lane >> 2);
-    const bool colv = (tj * TILE + 8 * warp) < n_valid;
-    double tacc[kTmaGroups][2];
-#pragma unroll
-    for (int i = 0; i < kTmaGroups; ++i) tacc[i][0] = tacc[i][1] = 0.0;
-    for (int kc = 0; kc < nk; ++kc) {
-      const int st = kc % kTmaStages;
-      mbar_wait(full_bar(st), (unsigned)(kc / kTmaStages) & 1u);
-      const double* a = stages + (size_t)st * 2 * kTmaOperandDoubles + aoffr;
-      const double* b = stages + (size_t)st * 2 * kTmaOperandDoubles + kTmaOperandDoubles + boffc;
-      if (colv) {
-#pragma unroll
-        for (int kk = 0; kk < KC; kk += 4) {
-          const double fb = b[kk * 8];
-#pragma unroll
-          for (int i = 0; i < kTmaGroups; ++i)
-            if (i < rows_valid) dmma884(tacc[i][0], tacc[i][1], a[(i * KC + kk) * 8], fb);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar(st));
-    }
-    if (!colv) return;
-#pragma unroll
-    for (int i = 0; i < kTmaGroups; ++i) {
-      if (i >= rows_valid) continue;
-      const int rl = 8 * i + (lane >> 2), cl = 8 * warp + 2 * (lane & 3);
-      if (SUB) {
-        const int r = ti * TILE + rl, c = tj * TILE + cl;
-        if (r >= n_store || c > r) continue;
-        const size_t off = (size_t)r * ld + c;
-        double* p = part + off;
-        const bool push = sp.world > 1 && tj * TILE < sp.push_cols;
-        if (c + 1 <= r) {
-          double2 v = *reinterpret_cast<double2*>(p);
-          v.x -= tacc[i][0];
-          v.y -= tacc[i][1];
-          *reinterpret_cast<double2*>(p) = v;
-          if (push)
-            for (int q = 0; q < sp.world; ++q)
-              if (q != sp.rank) *reinterpret_cast<double2*>(sp.peer[q] + off) = v;
-        } else {
-          const double v = *p - tacc[i][0];
-          *p = v;
-          if (push)
-            for (int q = 0; q < sp.world; ++q)
-              if (q != sp.rank) sp.peer[q][off] = v;
-        }
-      } else {
-        *reinterpret_cast<double2*>(part + (size_t)blockIdx.x * TILE * TILE + (size_t)rl * TILE + cl) =
-            make_double2(tacc[i][0], tacc[i][1]);
-      }
-    }
-    return;
-  }
+  // (A column-per-warp mapping for the thin tiles of a ragged last tile row was tried and dropped:
+  // with only 2 of 16 fragment rows to compute, the consumers outrun the three-stage TMA ring and
+  // wait for every chunk -- C3 went from 28.8 to 31.1 ms.  The square mapping below leaves such a
+  // tile at 0.34 of a full tile's time for 0.125 of its work.)
   const int wr = warp / WC, wc = warp % WC;
   int vm = 0, vn = 0;
 #pragma unroll
@@ -677,11 +618,7 @@ static double tile_weight(int TILE, int WR, int WC, int occ, int ti, int tj, int
   double load[4] = {0, 0, 0, 0};
   const bool tma_tile = TILE == kTmaTile && occ == 1 && syrk_feed_is_tma();
   const bool folded_diag = ti == tj && tma_tile;
-  if (tma_tile && ti != tj && n_valid - ti * TILE < TILE) {
-    // the TMA kernel's thin-tile mapping: every warp runs one DMMA per valid fragment row
-    const int rows_valid = (n_valid - ti * TILE + 7) / 8;
-    for (int k = 0; k < 4; ++k) load[k] = 4.0 * rows_valid;
-  }
+
   if (folded_diag) {
     // the TMA kernel's diagonal mapping: fragment rows r and 15 - r shared by two warps (9 + 8)
     const int rows_valid = std::min(16, (n_valid - ti * TILE + 7) / 8);
@@ -692,8 +629,7 @@ static double tile_weight(int TILE, int WR, int WC, int occ, int ti, int tj, int
       for (int j = 0; j < nfr; ++j) load[warp % 4] += ((j < n_hi ? r_hi : r_lo) < rows_valid) ? 1.0 : 0.0;
     }
   }
-  const bool thin_tma = tma_tile && ti != tj && n_valid - ti * TILE < TILE;
-  for (int warp = 0; warp < WR * WC && !folded_diag && !thin_tma; ++warp) {
+  for (int warp = 0; warp < WR * WC && !folded_diag; ++warp) {
     int wr = warp / WC, wc = warp % WC;
     bool live = true;
     if (ti == tj && WR == WC) {
