@@ -258,22 +258,26 @@ syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_c
 // chunk starts with all 16 warps issuing their LDGSTS (128 warp instructions, ~8 LSU cycles each)
 // right behind the block barrier, and the fragment loads of the chunk's first k-steps queue behind
 // them in the same LSU pipe -- ~1000 of every 8192 cycles the FP64 tensor pipes wait (tiles without
-// ragged edges ran at 85 % of the DMMA peak).  Here one extra warp is the producer: per chunk it
-// arms the stage's `full` mbarrier with the byte count and issues the tensor copies
-// (cp.async.bulk.tensor.2d -> SASS UTMALDG); the TMA engine writes shared memory and completes the
-// barrier, no LSU instruction and no block barrier is involved.  The 16 consumer warps wait on
-// `full`, run their DMMAs, and release the stage through the `empty` mbarrier (one arrival per warp).
+// ragged edges ran at 85 % of the DMMA peak).  Here the copies are tensor copies
+// (cp.async.bulk.tensor.2d -> SASS UTMALDG): ONE instruction per operand and chunk, issued by one
+// elected thread; the TMA engine writes shared memory and completes the stage's `full` mbarrier
+// with the byte count, no LSU copy instruction and no block barrier is involved.  All 16 warps wait
+// on `full`, run their DMMAs, and release the stage through the `empty` mbarrier (one arrival per
+// warp); the elected thread refills a stage one chunk after it was consumed, when every warp has
+// long moved on, so it practically never waits for `empty`.
 //
-// Shared-memory layout per stage and operand: [16 column groups][KC k-rows][8 doubles] -- one TMA
-// box {8 columns, KC rows} per group, written densely.  A warp's fragment load (4 k-rows x 8
-// columns of one group) is then 256 contiguous bytes: two conflict-free wavefronts, no padding.
-// Columns beyond n_valid lie outside the tensor and are zero-filled by the TMA unit.
-constexpr int kTmaTile = 128, kTmaKC = 32, kTmaStages = 3, kTmaGroups = kTmaTile / 8;
-constexpr int kTmaConsumerWarps = 16;
-constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;
-constexpr int kTmaOperandDoubles = kTmaKC * kTmaTile;                  // 4096 doubles = 32 KB
-constexpr int kTmaGroupBytes = kTmaKC * 8 * (int)sizeof(double);       // 2 KB per box
-constexpr size_t kTmaSmemBytes = (size_t)kTmaStages * 2 * kTmaOperandDoubles * sizeof(double) + 128 /*alignment*/ + 64 /*barriers*/;
+// Shared-memory layout per stage and operand: [KC k-rows][132 doubles] -- the box is 132 columns
+// wide, four more than the tile, so that the dense rows the TMA unit writes have the stride (1056 B
+// = 8 banks mod 32) that makes the DMMA fragment loads conflict-free: the 16 lanes of a half-warp
+// (4 k-rows x 4 columns) hit 16 distinct bank pairs.  (The first version used one box of 8 columns
+// per column group, [group][k][8]: ncu showed 2.2e9 bank conflicts -- k-rows 64 B apart collide two
+// by two -- and 32 UTMALDG per chunk.)  Columns beyond n_valid lie outside the tensor and are
+// zero-filled by the TMA unit.
+constexpr int kTmaTile = 128, kTmaKC = 32, kTmaStages = 3, kTmaLds = kTmaTile + 4;
+constexpr int kTmaThreads = 512;
+constexpr int kTmaOperandDoubles = kTmaKC * kTmaLds;                   // 4224 doubles = 33 KB
+constexpr unsigned kTmaOperandBytes = kTmaOperandDoubles * (unsigned)sizeof(double);
+constexpr size_t kTmaSmemBytes = (size_t)kTmaStages * 2 * kTmaOperandBytes + 128 /*alignment*/ + 64 /*barriers*/;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -305,13 +309,45 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
       : "memory");
 }
 
+// Epilogue of one accumulator pair at tile-local (rl, cl), cl even: the partial tile of the item,
+// or (SUB) subtracted in place from the lower triangle of S, with the peer stores of a divided update.
+template <bool SUB>
+__device__ __forceinline__ void syrk_store_pair(double v0, double v1, int ti, int tj, int rl, int cl, int ld,
+                                                int n_store, double* __restrict__ part, const SubSplit& sp) {
+  constexpr int TILE = kTmaTile;
+  if (SUB) {
+    const int r = ti * TILE + rl, c = tj * TILE + cl;
+    if (r >= n_store || c > r) return;
+    const size_t off = (size_t)r * ld + c;
+    double* p = part + off;
+    const bool push = sp.world > 1 && tj * TILE < sp.push_cols;
+    if (c + 1 <= r) {
+      double2 v = *reinterpret_cast<double2*>(p);
+      v.x -= v0;
+      v.y -= v1;
+      *reinterpret_cast<double2*>(p) = v;
+      if (push)
+        for (int q = 0; q < sp.world; ++q)
+          if (q != sp.rank) *reinterpret_cast<double2*>(sp.peer[q] + off) = v;
+    } else {
+      const double v = *p - v0;
+      *p = v;
+      if (push)
+        for (int q = 0; q < sp.world; ++q)
+          if (q != sp.rank) sp.peer[q][off] = v;
+    }
+  } else {
+    *reinterpret_cast<double2*>(part + (size_t)blockIdx.x * TILE * TILE + (size_t)rl * TILE + cl) = make_double2(v0, v1);
+  }
+}
+
 template <bool SUB>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, int64_t n_chunks,
                 const SyrkItem* __restrict__ items, double* __restrict__ part, const ba_lm_state* ctl,
                 int n_store, SubSplit sp) {
   if (ctl && ctl->done) return;
-  constexpr int TILE = kTmaTile, KC = kTmaKC, WR = 4, WC = 4;
+  constexpr int TILE = kTmaTile, KC = kTmaKC, LDS = kTmaLds, WR = 4, WC = 4;
   constexpr int WM = TILE / WR, WN = TILE / WC, FM = WM / 8, FN = WN / 8;
   extern __shared__ unsigned char smem_raw[];
 
@@ -331,53 +367,50 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
 
   // carve shared memory: operand stages (128-byte aligned for the TMA unit), then the mbarriers
   const unsigned base = (smem_u32(smem_raw) + 127u) & ~127u;
-  double* stages = reinterpret_cast<double*>(smem_raw + (base - smem_u32(smem_raw)));
-  const unsigned bars = base + kTmaStages * 2 * kTmaOperandDoubles * (unsigned)sizeof(double);
+  const double* stages = reinterpret_cast<const double*>(smem_raw + (base - smem_u32(smem_raw)));
+  const unsigned bars = base + kTmaStages * 2 * kTmaOperandBytes;
   auto full_bar = [&](int st) { return bars + 8u * st; };
   auto empty_bar = [&](int st) { return bars + 8u * (kTmaStages + st); };
+  const unsigned stage_bytes = (diag ? 1u : 2u) * kTmaOperandBytes;
+  // chunk `kc` of this item into stage kc % kTmaStages (one elected thread)
+  auto issue = [&](int kc) {
+    const int st = kc % kTmaStages;
+    const unsigned dst = base + (unsigned)st * 2u * kTmaOperandBytes;
+    const int row = (int)((c_lo + kc) * KC);
+    mbar_arrive_expect_tx(full_bar(st), stage_bytes);
+    tma_load_2d(dst, &tmap, ti * TILE, row, full_bar(st));
+    if (!diag) tma_load_2d(dst + kTmaOperandBytes, &tmap, tj * TILE, row, full_bar(st));
+  };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int st = 0; st < kTmaStages; ++st) {
       mbar_init(full_bar(st), 1);
-      mbar_init(empty_bar(st), kTmaConsumerWarps);
+      mbar_init(empty_bar(st), kTmaThreads / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int kc = 0; kc < kTmaStages && kc < nk; ++kc) issue(kc);
   }
   __syncthreads();
-
-  if (warp == kTmaConsumerWarps) {
-    // ---- producer warp: lane g < 16 copies column group g of A, lane 16 + g that of B -----------
-    // column groups of A beyond the valid part of a ragged last tile row are not copied at all
-    // (nobody reads them); B of an off-diagonal tile is always a full tile column
-    const int a_groups = min(kTmaGroups, (n_valid - ti * TILE + 7) / 8);
-    const unsigned stage_bytes = (unsigned)(a_groups + (diag ? 0 : kTmaGroups)) * kTmaGroupBytes;
-    const int grp = lane & (kTmaGroups - 1);
-    const bool issuer = lane < kTmaGroups ? grp < a_groups : !diag;
-    const int col = (lane < kTmaGroups ? ti : tj) * TILE + 8 * grp;
-    const unsigned dst_off = (lane < kTmaGroups ? 0u : (unsigned)kTmaOperandDoubles * 8u) + (unsigned)grp * kTmaGroupBytes;
-    for (int kc = 0; kc < nk; ++kc) {
-      const int st = kc % kTmaStages;
-      const unsigned use = (unsigned)(kc / kTmaStages);
-      if (use > 0) mbar_wait(empty_bar(st), (use - 1) & 1u);  // the consumers are done with the previous use
-      if (lane == 0) mbar_arrive_expect_tx(full_bar(st), stage_bytes);
+  // Before chunk kc is computed the elected thread refills the stage of chunk kc - 1 with chunk
+  // kc + 2 (every warp is done with chunk kc - 1 or about to be: the wait on `empty` is short).
+  auto refill = [&](int kc) {
+    if (warp == 0) {
+      if (lane == 0 && kc >= 1 && kc + kTmaStages - 1 < nk) {
+        mbar_wait(empty_bar((kc - 1) % kTmaStages), (unsigned)((kc - 1) / kTmaStages) & 1u);
+        issue(kc + kTmaStages - 1);
+      }
       __syncwarp();
-      if (issuer)
-        tma_load_2d(base + (unsigned)st * 2u * kTmaOperandDoubles * 8u + dst_off, &tmap, col,
-                    (int)((c_lo + kc) * KC), full_bar(st));
     }
-    return;
-  }
-
-  // ---- consumer warps -----------------------------------------------------------------------------
+  };
   const int kq = lane & 3;
+
   if (diag) {
     // Diagonal tile: only the 136 fragments (8 x 8) on or below the diagonal of the 16 x 16 fragment
     // grid are needed.  Fragment rows r and 15 - r together hold 17 of them; the pair is shared by
     // two warps, one taking nine fragments (row 15 - r, columns 0..8), the other eight (the rest of
-    // row 15 - r and all of row r).  Which warp of a pair takes nine alternates so that every
-    // scheduler partition (warp % 4) carries 34 fragments per k-step: 0.53 of a full tile's 64
-    // instead of the 0.75 of the square sub-tile mapping (3 of 4 rounds).
+    // row 15 - r and all of row r); which warp of a pair takes nine alternates so that every
+    // scheduler partition (warp % 4) carries 34 fragments per k-step.
     const int pr = warp >> 1;
     const bool nine = (((warp & 1) ^ ((warp >> 2) & 1)) == 0);
     const int r_hi = 15 - pr, r_lo = pr;
@@ -387,33 +420,33 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
     const int frag_rows_valid = (n_valid - ti * TILE + 7) / 8;  // ragged last tile
     int boffj[9];
     bool usej[9];
+    bool any = false;
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
       const bool hi = j < n_hi;
       const int rf = hi ? r_hi : r_lo;
       const int cf = hi ? c_hi0 + j : j - n_hi;
       usej[j] = j < nfr && rf < frag_rows_valid;
-      boffj[j] = (cf * KC + kq) * 8 + (lane >> 2);
+      any |= usej[j];
+      boffj[j] = kq * LDS + 8 * cf + (lane >> 2);
     }
-    const int aoff_hi = (r_hi * KC + kq) * 8 + (lane >> 2);
-    const int aoff_lo = (r_lo * KC + kq) * 8 + (lane >> 2);
-    bool any = false;
-#pragma unroll
-    for (int j = 0; j < 9; ++j) any |= usej[j];
+    const int aoff_hi = kq * LDS + 8 * r_hi + (lane >> 2);
+    const int aoff_lo = kq * LDS + 8 * r_lo + (lane >> 2);
     double dacc[9][2];
 #pragma unroll
     for (int j = 0; j < 9; ++j) dacc[j][0] = dacc[j][1] = 0.0;
     for (int kc = 0; kc < nk; ++kc) {
+      refill(kc);
       const int st = kc % kTmaStages;
       mbar_wait(full_bar(st), (unsigned)(kc / kTmaStages) & 1u);
       const double* a = stages + (size_t)st * 2 * kTmaOperandDoubles;
       if (any) {
 #pragma unroll
         for (int kk = 0; kk < KC; kk += 4) {
-          const double fa_hi = a[aoff_hi + kk * 8], fa_lo = a[aoff_lo + kk * 8];
+          const double fa_hi = a[aoff_hi + kk * LDS], fa_lo = a[aoff_lo + kk * LDS];
           double fb[9];
 #pragma unroll
-          for (int j = 0; j < 9; ++j) fb[j] = a[boffj[j] + kk * 8];
+          for (int j = 0; j < 9; ++j) fb[j] = a[boffj[j] + kk * LDS];
 #pragma unroll
           for (int j = 0; j < 9; ++j)
             if (usej[j]) dmma884(dacc[j][0], dacc[j][1], j < n_hi ? fa_hi : fa_lo, fb[j]);
@@ -426,40 +459,16 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
     for (int j = 0; j < 9; ++j) {
       if (!usej[j]) continue;
       const bool hi = j < n_hi;
-      const int rl = 8 * (hi ? r_hi : r_lo) + (lane >> 2);             // row / column inside the tile
-      const int cl = 8 * (hi ? c_hi0 + j : j - n_hi) + 2 * (lane & 3);
-      if (SUB) {
-        const int r = ti * TILE + rl, c = ti * TILE + cl;
-        if (r >= n_store || c > r) continue;
-        const size_t off = (size_t)r * ld + c;
-        double* p = part + off;
-        const bool push = sp.world > 1 && ti * TILE < sp.push_cols;
-        if (c + 1 <= r) {
-          double2 v = *reinterpret_cast<double2*>(p);
-          v.x -= dacc[j][0];
-          v.y -= dacc[j][1];
-          *reinterpret_cast<double2*>(p) = v;
-          if (push)
-            for (int q = 0; q < sp.world; ++q)
-              if (q != sp.rank) *reinterpret_cast<double2*>(sp.peer[q] + off) = v;
-        } else {
-          const double v = *p - dacc[j][0];
-          *p = v;
-          if (push)
-            for (int q = 0; q < sp.world; ++q)
-              if (q != sp.rank) sp.peer[q][off] = v;
-        }
-      } else {
-        *reinterpret_cast<double2*>(part + (size_t)blockIdx.x * TILE * TILE + (size_t)rl * TILE + cl) =
-            make_double2(dacc[j][0], dacc[j][1]);
-      }
+      syrk_store_pair<SUB>(dacc[j][0], dacc[j][1], ti, ti, 8 * (hi ? r_hi : r_lo) + (lane >> 2),
+                           8 * (hi ? c_hi0 + j : j - n_hi) + 2 * (lane & 3), ld, n_store, part, sp);
     }
     return;
   }
+
   // (A column-per-warp mapping for the thin tiles of a ragged last tile row was tried and dropped:
-  // with only 2 of 16 fragment rows to compute, the consumers outrun the three-stage TMA ring and
-  // wait for every chunk -- C3 went from 28.8 to 31.1 ms.  The square mapping below leaves such a
-  // tile at 0.34 of a full tile's time for 0.125 of its work.)
+  // with only 2 of 16 fragment rows to compute, the warps outrun the three-stage TMA ring and wait
+  // for every chunk -- C3 went from 28.8 to 31.1 ms.  The square mapping below leaves such a tile at
+  // 0.34 of a full tile's time for 0.125 of its work.)
   const int wr = warp / WC, wc = warp % WC;
   int vm = 0, vn = 0;
 #pragma unroll
@@ -467,9 +476,8 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
 #pragma unroll
   for (int j = 0; j < FN; ++j) vn += (tj * TILE + wc * WN + 8 * j) < n_valid;
   const bool full = vm == FM && vn == FN;
-  // element (k, column group g, column c) of a stage operand sits at (g * KC + k) * 8 + c
-  const int aoff = (wr * FM * KC + kq) * 8 + (lane >> 2);
-  const int boff = (wc * FN * KC + kq) * 8 + (lane >> 2);
+  const int aoff = kq * LDS + wr * WM + (lane >> 2);
+  const int boff = kq * LDS + wc * WN + (lane >> 2);
 
   double acc[FM][FN][2];
 #pragma unroll
@@ -478,18 +486,19 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
     for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   for (int kc = 0; kc < nk; ++kc) {
+    refill(kc);
     const int st = kc % kTmaStages;
     mbar_wait(full_bar(st), (unsigned)(kc / kTmaStages) & 1u);
     const double* a = stages + (size_t)st * 2 * kTmaOperandDoubles + aoff;
-    const double* b = stages + (size_t)st * 2 * kTmaOperandDoubles + (diag ? 0 : kTmaOperandDoubles) + boff;
+    const double* b = stages + (size_t)st * 2 * kTmaOperandDoubles + kTmaOperandDoubles + boff;
     if (full) {
 #pragma unroll
       for (int kk = 0; kk < KC; kk += 4) {
         double fa[FM], fb[FN];
 #pragma unroll
-        for (int i = 0; i < FM; ++i) fa[i] = a[(i * KC + kk) * 8];
+        for (int i = 0; i < FM; ++i) fa[i] = a[kk * LDS + 8 * i];
 #pragma unroll
-        for (int j = 0; j < FN; ++j) fb[j] = b[(j * KC + kk) * 8];
+        for (int j = 0; j < FN; ++j) fb[j] = b[kk * LDS + 8 * j];
 #pragma unroll
         for (int i = 0; i < FM; ++i)
 #pragma unroll
@@ -500,9 +509,9 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
       for (int kk = 0; kk < KC; kk += 4) {
         double fa[FM], fb[FN];
 #pragma unroll
-        for (int i = 0; i < FM; ++i) fa[i] = a[(i * KC + kk) * 8];
+        for (int i = 0; i < FM; ++i) fa[i] = a[kk * LDS + 8 * i];
 #pragma unroll
-        for (int j = 0; j < FN; ++j) fb[j] = b[(j * KC + kk) * 8];
+        for (int j = 0; j < FN; ++j) fb[j] = b[kk * LDS + 8 * j];
 #pragma unroll
         for (int i = 0; i < FM; ++i)
 #pragma unroll
@@ -516,42 +525,11 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
 
   const int orow = wr * WM + (lane >> 2);
   const int ocol = wc * WN + 2 * (lane & 3);
-  if (SUB) {
-    // S -= acc on the lower triangle; an accumulator pair sits at (r, c), (r, c + 1), c even
-#pragma unroll
-    for (int i = 0; i < FM; ++i)
-#pragma unroll
-      for (int j = 0; j < FN; ++j) {
-        const int r = ti * TILE + orow + 8 * i, c = tj * TILE + ocol + 8 * j;
-        if (r >= n_store || c > r) continue;
-        const size_t off = (size_t)r * ld + c;
-        double* p = part + off;
-        const bool push = sp.world > 1 && tj * TILE < sp.push_cols;
-        if (c + 1 <= r) {
-          double2 v = *reinterpret_cast<double2*>(p);
-          v.x -= acc[i][j][0];
-          v.y -= acc[i][j][1];
-          *reinterpret_cast<double2*>(p) = v;
-          if (push)
-            for (int q = 0; q < sp.world; ++q)
-              if (q != sp.rank) *reinterpret_cast<double2*>(sp.peer[q] + off) = v;
-        } else {
-          const double v = *p - acc[i][j][0];
-          *p = v;
-          if (push)
-            for (int q = 0; q < sp.world; ++q)
-              if (q != sp.rank) sp.peer[q][off] = v;
-        }
-      }
-    return;
-  }
-  double* out = part + (size_t)blockIdx.x * TILE * TILE;
 #pragma unroll
   for (int i = 0; i < FM; ++i)
 #pragma unroll
     for (int j = 0; j < FN; ++j)
-      *reinterpret_cast<double2*>(out + (size_t)(orow + 8 * i) * TILE + ocol + 8 * j) =
-          make_double2(acc[i][j][0], acc[i][j][1]);
+      syrk_store_pair<SUB>(acc[i][j][0], acc[i][j][1], ti, tj, orow + 8 * i, ocol + 8 * j, ld, n_store, part, sp);
 }
 
 // P[tile] = sum of the tile's items in a fixed order (ascending k range), restricted to the valid
@@ -810,13 +788,14 @@ static EncodeTiledFn tensor_map_encoder() {
   return fn;
 }
 
-// k-major operand `base` [rows][ld] doubles, `cols` valid columns: boxes of 8 columns x kTmaKC rows.
+// k-major operand `base` [rows][ld] doubles, `cols` valid columns: boxes of kTmaLds (132) columns x
+// kTmaKC rows (see syrk_tma_kernel for the four extra columns).
 static int make_operand_map(CUtensorMap* map, const double* base, int cols, int64_t rows, int ld) {
   EncodeTiledFn enc = tensor_map_encoder();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return BA_ERR_CUDA; }
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
-  const cuuint32_t box[2] = {8, (cuuint32_t)kTmaKC};
+  const cuuint32_t box[2] = {(cuuint32_t)kTmaLds, (cuuint32_t)kTmaKC};
   const cuuint32_t estride[2] = {1, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box,
                          estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
