@@ -70,6 +70,8 @@ enum ProfGroup { PG_K1 = 0, PG_K2, PG_K3, PG_K4, PG_COST, PG_OTHER, PG_SYRK, PG_
 // One CTA of the dense Schur product: tile (ti, tj) of P and the k-chunks [c_lo, c_hi) of Y^T.
 struct SyrkItem {
   int ti, tj, c_lo, c_hi;
+  int slot2;  // >= 0: a "tall" item also computes the ragged rows below its tile (the thin tile
+              // (ti + 1, tj)); their partial results go to this slot of the partial-tile store
 };
 
 struct Comm;  // peer-memory exchange of a sharded run (comm_peer.cu)

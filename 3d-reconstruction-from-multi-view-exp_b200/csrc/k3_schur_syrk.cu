@@ -273,11 +273,22 @@ syrk_dmma_kernel(const double* __restrict__ Yt, int ld, int n_valid, int64_t n_c
 // per column group, [group][k][8]: ncu showed 2.2e9 bank conflicts -- k-rows 64 B apart collide two
 // by two -- and 32 UTMALDG per chunk.)  Columns beyond n_valid lie outside the tensor and are
 // zero-filled by the TMA unit.
-constexpr int kTmaTile = 128, kTmaKC = 32, kTmaStages = 3, kTmaLds = kTmaTile + 4;
+//
+// Ragged last tile row.  With n_pad = 1808 (200 cameras) the last tile row has 16 valid rows: as
+// tiles of their own those 15 thin tiles cost 4.9 % of the kernel for 1.9 % of its flops (each is
+// bound by the latency of the three-stage ring, not by its DMMAs).  When at most kTmaTallRows rows
+// are left over, the tiles of the row above are "tall": their A box is 148 columns wide (for every
+// tile -- the 16 extra columns cost nothing measurable), and every warp computes two more fragments
+// -- fragment row 16 or 17 against two of the B fragments it already holds.  Only the two thin
+// tiles next to the diagonal remain items of their own.
+constexpr int kTmaTile = 128, kTmaKC = 32, kTmaStages = 3, kTmaTallRows = 16;
+constexpr int kTmaLda = kTmaTile + kTmaTallRows + 4, kTmaLdb = kTmaTile + 4;   // 148, 132: both = 8 banks mod 32
 constexpr int kTmaThreads = 512;
-constexpr int kTmaOperandDoubles = kTmaKC * kTmaLds;                   // 4224 doubles = 33 KB
-constexpr unsigned kTmaOperandBytes = kTmaOperandDoubles * (unsigned)sizeof(double);
-constexpr size_t kTmaSmemBytes = (size_t)kTmaStages * 2 * kTmaOperandBytes + 128 /*alignment*/ + 64 /*barriers*/;
+constexpr int kTmaADoubles = kTmaKC * kTmaLda, kTmaBDoubles = kTmaKC * kTmaLdb;
+constexpr unsigned kTmaABytes = kTmaADoubles * (unsigned)sizeof(double);    // 37 888
+constexpr unsigned kTmaBBytes = kTmaBDoubles * (unsigned)sizeof(double);    // 33 792
+constexpr unsigned kTmaStageBytes = kTmaABytes + kTmaBBytes;                // 71 680
+constexpr size_t kTmaSmemBytes = (size_t)kTmaStages * kTmaStageBytes + 128 /*alignment*/ + 64 /*barriers*/;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -313,7 +324,8 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
 // or (SUB) subtracted in place from the lower triangle of S, with the peer stores of a divided update.
 template <bool SUB>
 __device__ __forceinline__ void syrk_store_pair(double v0, double v1, int ti, int tj, int rl, int cl, int ld,
-                                                int n_store, double* __restrict__ part, const SubSplit& sp) {
+                                                int n_store, double* __restrict__ part, const SubSplit& sp,
+                                                int slot = -1) {
   constexpr int TILE = kTmaTile;
   if (SUB) {
     const int r = ti * TILE + rl, c = tj * TILE + cl;
@@ -337,21 +349,24 @@ __device__ __forceinline__ void syrk_store_pair(double v0, double v1, int ti, in
           if (q != sp.rank) sp.peer[q][off] = v;
     }
   } else {
-    *reinterpret_cast<double2*>(part + (size_t)blockIdx.x * TILE * TILE + (size_t)rl * TILE + cl) = make_double2(v0, v1);
+    // rows >= TILE of a tall item belong to the thin tile below: its own slot, rows from 0
+    const size_t s = slot >= 0 ? (size_t)slot : (size_t)blockIdx.x;
+    const int r = slot >= 0 ? rl - TILE : rl;
+    *reinterpret_cast<double2*>(part + s * TILE * TILE + (size_t)r * TILE + cl) = make_double2(v0, v1);
   }
 }
 
 template <bool SUB>
 __global__ void __launch_bounds__(kTmaThreads, 1)
-syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, int64_t n_chunks,
-                const SyrkItem* __restrict__ items, double* __restrict__ part, const ba_lm_state* ctl,
-                int n_store, SubSplit sp) {
+syrk_tma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, int ld,
+                int n_valid, int64_t n_chunks, const SyrkItem* __restrict__ items, double* __restrict__ part,
+                const ba_lm_state* ctl, int n_store, SubSplit sp) {
   if (ctl && ctl->done) return;
-  constexpr int TILE = kTmaTile, KC = kTmaKC, LDS = kTmaLds, WR = 4, WC = 4;
+  constexpr int TILE = kTmaTile, KC = kTmaKC, LDA = kTmaLda, LDB = kTmaLdb, WR = 4, WC = 4;
   constexpr int WM = TILE / WR, WN = TILE / WC, FM = WM / 8, FN = WN / 8;
   extern __shared__ unsigned char smem_raw[];
 
-  int ti, tj;
+  int ti, tj, slot2 = -1;
   int64_t c_lo, c_hi;
   if (SUB) {
     tile_from_linear(blockIdx.x, ti, tj);
@@ -360,26 +375,28 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
     c_hi = n_chunks;
   } else {
     const SyrkItem it = items[blockIdx.x];
-    ti = it.ti; tj = it.tj; c_lo = it.c_lo; c_hi = it.c_hi;
+    ti = it.ti; tj = it.tj; c_lo = it.c_lo; c_hi = it.c_hi; slot2 = it.slot2;
   }
   const bool diag = ti == tj;
+  const bool tall = slot2 >= 0;
   const int nk = (int)(c_hi > c_lo ? c_hi - c_lo : 0);
 
   // carve shared memory: operand stages (128-byte aligned for the TMA unit), then the mbarriers
   const unsigned base = (smem_u32(smem_raw) + 127u) & ~127u;
   const double* stages = reinterpret_cast<const double*>(smem_raw + (base - smem_u32(smem_raw)));
-  const unsigned bars = base + kTmaStages * 2 * kTmaOperandBytes;
+  constexpr int kStageDoubles = kTmaADoubles + kTmaBDoubles;
+  const unsigned bars = base + kTmaStages * kTmaStageBytes;
   auto full_bar = [&](int st) { return bars + 8u * st; };
   auto empty_bar = [&](int st) { return bars + 8u * (kTmaStages + st); };
-  const unsigned stage_bytes = (diag ? 1u : 2u) * kTmaOperandBytes;
+  const unsigned stage_bytes = kTmaABytes + (diag ? 0u : kTmaBBytes);
   // chunk `kc` of this item into stage kc % kTmaStages (one elected thread)
   auto issue = [&](int kc) {
     const int st = kc % kTmaStages;
-    const unsigned dst = base + (unsigned)st * 2u * kTmaOperandBytes;
+    const unsigned dst = base + (unsigned)st * kTmaStageBytes;
     const int row = (int)((c_lo + kc) * KC);
     mbar_arrive_expect_tx(full_bar(st), stage_bytes);
-    tma_load_2d(dst, &tmap, ti * TILE, row, full_bar(st));
-    if (!diag) tma_load_2d(dst + kTmaOperandBytes, &tmap, tj * TILE, row, full_bar(st));
+    tma_load_2d(dst, &tmapA, ti * TILE, row, full_bar(st));
+    if (!diag) tma_load_2d(dst + kTmaABytes, &tmapB, tj * TILE, row, full_bar(st));
   };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -428,10 +445,10 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
       const int cf = hi ? c_hi0 + j : j - n_hi;
       usej[j] = j < nfr && rf < frag_rows_valid;
       any |= usej[j];
-      boffj[j] = kq * LDS + 8 * cf + (lane >> 2);
+      boffj[j] = kq * LDA + 8 * cf + (lane >> 2);
     }
-    const int aoff_hi = kq * LDS + 8 * r_hi + (lane >> 2);
-    const int aoff_lo = kq * LDS + 8 * r_lo + (lane >> 2);
+    const int aoff_hi = kq * LDA + 8 * r_hi + (lane >> 2);
+    const int aoff_lo = kq * LDA + 8 * r_lo + (lane >> 2);
     double dacc[9][2];
 #pragma unroll
     for (int j = 0; j < 9; ++j) dacc[j][0] = dacc[j][1] = 0.0;
@@ -439,14 +456,14 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
       refill(kc);
       const int st = kc % kTmaStages;
       mbar_wait(full_bar(st), (unsigned)(kc / kTmaStages) & 1u);
-      const double* a = stages + (size_t)st * 2 * kTmaOperandDoubles;
+      const double* a = stages + (size_t)st * kStageDoubles;
       if (any) {
 #pragma unroll
         for (int kk = 0; kk < KC; kk += 4) {
-          const double fa_hi = a[aoff_hi + kk * LDS], fa_lo = a[aoff_lo + kk * LDS];
+          const double fa_hi = a[aoff_hi + kk * LDA], fa_lo = a[aoff_lo + kk * LDA];
           double fb[9];
 #pragma unroll
-          for (int j = 0; j < 9; ++j) fb[j] = a[boffj[j] + kk * LDS];
+          for (int j = 0; j < 9; ++j) fb[j] = a[boffj[j] + kk * LDA];
 #pragma unroll
           for (int j = 0; j < 9; ++j)
             if (usej[j]) dmma884(dacc[j][0], dacc[j][1], j < n_hi ? fa_hi : fa_lo, fb[j]);
@@ -476,29 +493,52 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
 #pragma unroll
   for (int j = 0; j < FN; ++j) vn += (tj * TILE + wc * WN + 8 * j) < n_valid;
   const bool full = vm == FM && vn == FN;
-  const int aoff = kq * LDS + wr * WM + (lane >> 2);
-  const int boff = kq * LDS + wc * WN + (lane >> 2);
+  const int aoff = kq * LDA + wr * WM + (lane >> 2);
+  const int boff = kq * LDB + wc * WN + (lane >> 2);
+  // tall item: this warp's two extra fragments -- fragment row 16 + (wr & 1) of A against its B
+  // fragments 2 (wr >> 1) and 2 (wr >> 1) + 1
+  const int xoff = kq * LDA + TILE + 8 * (wr & 1) + (lane >> 2);
+  const int xj = 2 * (wr >> 1);
+  const bool xvalid = tall && (ti + 1) * TILE + 8 * (wr & 1) < n_valid;
 
-  double acc[FM][FN][2];
+  double acc[FM][FN][2], xacc[2][2];
 #pragma unroll
   for (int i = 0; i < FM; ++i)
 #pragma unroll
     for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  xacc[0][0] = xacc[0][1] = xacc[1][0] = xacc[1][1] = 0.0;
 
   for (int kc = 0; kc < nk; ++kc) {
     refill(kc);
     const int st = kc % kTmaStages;
     mbar_wait(full_bar(st), (unsigned)(kc / kTmaStages) & 1u);
-    const double* a = stages + (size_t)st * 2 * kTmaOperandDoubles + aoff;
-    const double* b = stages + (size_t)st * 2 * kTmaOperandDoubles + kTmaOperandDoubles + boff;
-    if (full) {
+    const double* a = stages + (size_t)st * kStageDoubles + aoff;
+    const double* b = stages + (size_t)st * kStageDoubles + kTmaADoubles + boff;
+    if (full && xvalid) {
+      const double* x = stages + (size_t)st * kStageDoubles + xoff;
 #pragma unroll
       for (int kk = 0; kk < KC; kk += 4) {
         double fa[FM], fb[FN];
 #pragma unroll
-        for (int i = 0; i < FM; ++i) fa[i] = a[kk * LDS + 8 * i];
+        for (int i = 0; i < FM; ++i) fa[i] = a[kk * LDA + 8 * i];
 #pragma unroll
-        for (int j = 0; j < FN; ++j) fb[j] = b[kk * LDS + 8 * j];
+        for (int j = 0; j < FN; ++j) fb[j] = b[kk * LDB + 8 * j];
+        const double fx = x[kk * LDA];
+#pragma unroll
+        for (int i = 0; i < FM; ++i)
+#pragma unroll
+          for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+        dmma884(xacc[0][0], xacc[0][1], fx, xj == 0 ? fb[0] : fb[2]);
+        dmma884(xacc[1][0], xacc[1][1], fx, xj == 0 ? fb[1] : fb[3]);
+      }
+    } else if (full) {
+#pragma unroll
+      for (int kk = 0; kk < KC; kk += 4) {
+        double fa[FM], fb[FN];
+#pragma unroll
+        for (int i = 0; i < FM; ++i) fa[i] = a[kk * LDA + 8 * i];
+#pragma unroll
+        for (int j = 0; j < FN; ++j) fb[j] = b[kk * LDB + 8 * j];
 #pragma unroll
         for (int i = 0; i < FM; ++i)
 #pragma unroll
@@ -509,9 +549,9 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
       for (int kk = 0; kk < KC; kk += 4) {
         double fa[FM], fb[FN];
 #pragma unroll
-        for (int i = 0; i < FM; ++i) fa[i] = a[kk * LDS + 8 * i];
+        for (int i = 0; i < FM; ++i) fa[i] = a[kk * LDA + 8 * i];
 #pragma unroll
-        for (int j = 0; j < FN; ++j) fb[j] = b[kk * LDS + 8 * j];
+        for (int j = 0; j < FN; ++j) fb[j] = b[kk * LDB + 8 * j];
 #pragma unroll
         for (int i = 0; i < FM; ++i)
 #pragma unroll
@@ -530,6 +570,13 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ld, int n_valid, i
 #pragma unroll
     for (int j = 0; j < FN; ++j)
       syrk_store_pair<SUB>(acc[i][j][0], acc[i][j][1], ti, tj, orow + 8 * i, ocol + 8 * j, ld, n_store, part, sp);
+  if (xvalid) {
+    const int xr = TILE + 8 * (wr & 1) + (lane >> 2);
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      syrk_store_pair<SUB>(xacc[e][0], xacc[e][1], ti, tj, xr, wc * WN + 8 * (xj + e) + 2 * (lane & 3), ld, n_store,
+                           part, sp, slot2);
+  }
 }
 
 // P[tile] = sum of the tile's items in a fixed order (ascending k range), restricted to the valid
@@ -585,6 +632,12 @@ static inline int syrk_kc(int tile) { return tile == 128 ? 32 : 16; }
 static inline int syrk_occupancy(int tile) { return tile == 128 ? 1 : 4; }
 
 int syrk_feed_is_tma();
+// The planner's view of the feed: BA_SYRK_PLAN_ASSUME_TMA=1 lets the host-only self-check of the
+// plan (ba_syrk_plan_info, run on CPU boxes) exercise the TMA kernel's tile shapes.
+static bool plan_for_tma() {
+  static const bool assume = std::getenv("BA_SYRK_PLAN_ASSUME_TMA") != nullptr;
+  return assume || syrk_feed_is_tma();
+}
 
 // Relative duration of a tile per k-row (1 = full tile), mirroring the kernel's warp mapping:
 // edge tiles skip the 8x8 fragments beyond n_valid, diagonal tiles the sub-tiles above the
@@ -594,7 +647,7 @@ int syrk_feed_is_tma();
 static double tile_weight(int TILE, int WR, int WC, int occ, int ti, int tj, int n_valid, int64_t k_pad = 0) {
   const int WM = TILE / WR, WN = TILE / WC, FM = WM / 8, FN = WN / 8;
   double load[4] = {0, 0, 0, 0};
-  const bool tma_tile = TILE == kTmaTile && occ == 1 && syrk_feed_is_tma();
+  const bool tma_tile = TILE == kTmaTile && occ == 1 && plan_for_tma();
   const bool folded_diag = ti == tj && tma_tile;
 
   if (folded_diag) {
@@ -639,7 +692,7 @@ static double tile_weight(int TILE, int WR, int WC, int occ, int ti, int tj, int
   // 1.0: 0.286 ms, 0.5: 0.298, 0.3: 0.311 -- with two waves the schedule is decided by whole items,
   // and uniform cuts pack them best.
   const bool small_operand = k_pad > 0 && (double)k_pad * n_valid * 8.0 <= 256.0 * 1024 * 1024;
-  double floor_w = occ == 1 ? (syrk_feed_is_tma() ? (small_operand ? 1.0 : 0.5) : 0.75) : 1.0;
+  double floor_w = occ == 1 ? (plan_for_tma() ? (small_operand ? 1.0 : 0.5) : 0.75) : 1.0;
   if (const char* f = std::getenv("BA_SYRK_FLOOR")) floor_w = std::atof(f);  // tuning experiments only
   return w > floor_w ? w : floor_w;
 }
@@ -647,9 +700,21 @@ static double tile_weight(int TILE, int WR, int WC, int occ, int ti, int tj, int
 struct SyrkPlan {
   std::vector<SyrkItem> items;       // launch order: ascending k range, then tile
   std::vector<int> tile_first;       // [n_tiles + 1]
-  std::vector<int> tile_items;       // item index per (tile, piece), pieces in ascending k order
+  std::vector<int> tile_items;       // partial-tile slot per (tile, piece), pieces in ascending k order
+  int n_slots = 0;                   // partial tiles: one per item + one per tall item (its thin tile below)
+  int tall_row = -1;                 // tile row whose off-diagonal tiles also compute the ragged rows below
   double makespan = 0.0;             // modelled duration in k-rows of a full tile on one SM slot
 };
+
+// The ragged last tile row is folded into the row above (see kTmaTallRows) when the TMA kernel runs
+// and at most kTmaTallRows rows are left over: returns that row (nt1 - 2), else -1.
+static int tall_tile_row(int n_pad, int TILE, int occ) {
+  static const bool off = std::getenv("BA_SYRK_NO_TALL") != nullptr;  // A/B timing only
+  const int nt1 = (n_pad + TILE - 1) / TILE;
+  const int left = n_pad - (nt1 - 1) * TILE;
+  if (off || TILE != kTmaTile || occ != 1 || !plan_for_tma() || nt1 < 3 || left > kTmaTallRows) return -1;
+  return nt1 - 2;
+}
 
 // Cut every tile's K range into pieces so that all CTAs take about the same time and their number
 // fills whole waves of SM slots: pieces(t) ~ weight(t) x S.  S is chosen by simulating the block
@@ -665,8 +730,17 @@ static SyrkPlan plan_syrk(int n_pad, int TILE, int WR, int WC, int64_t k_pad, in
   const int64_t n_chunks = k_pad / KC;
   const int slots = num_sms * occ;
   std::vector<double> w(n_tiles);
+  const int tall_row = tall_tile_row(n_pad, TILE, occ);
+  // absorbed[t]: thin tile (nt1 - 1, tj), tj < tall_row: computed by the tall tile (tall_row, tj)
+  std::vector<char> absorbed(n_tiles, 0), is_tall(n_tiles, 0);
   for (int t = 0, ti = 0; ti < nt1; ++ti)
-    for (int tj = 0; tj <= ti; ++tj, ++t) w[t] = tile_weight(TILE, WR, WC, occ, ti, tj, n_pad, k_pad);
+    for (int tj = 0; tj <= ti; ++tj, ++t) {
+      w[t] = tile_weight(TILE, WR, WC, occ, ti, tj, n_pad, k_pad);
+      if (tall_row >= 0 && tj < tall_row) {
+        if (ti == tall_row) { is_tall[t] = 1; w[t] *= 1.0 + 2.0 / 16.0; }  // two more fragments per warp
+        if (ti == nt1 - 1) absorbed[t] = 1;
+      }
+    }
   const int64_t min_chunks = std::max<int64_t>(1, 512 / KC);
   const int64_t s_max = std::max<int64_t>(1, n_chunks / min_chunks);
   const int64_t slab_cap = (int64_t)48 << 20;
@@ -680,6 +754,7 @@ static SyrkPlan plan_syrk(int n_pad, int TILE, int WR, int WC, int64_t k_pad, in
     std::vector<Piece> pieces;
     std::vector<int> count(n_tiles);
     for (int t = 0; t < n_tiles; ++t) {
+      if (absorbed[t]) { count[t] = 0; continue; }
       int64_t p = (int64_t)std::llround(w[t] * (double)S);
       p = std::max<int64_t>(1, std::min<int64_t>(p, s_max));
       const int64_t cps = (n_chunks + p - 1) / p;
@@ -704,16 +779,29 @@ static SyrkPlan plan_syrk(int n_pad, int TILE, int WR, int WC, int64_t k_pad, in
     if (out) {
       out->items.clear();
       out->tile_first.assign(n_tiles + 1, 0);
-      for (int t = 0; t < n_tiles; ++t) out->tile_first[t + 1] = out->tile_first[t] + count[t];
-      out->tile_items.assign(out->tile_first[n_tiles], 0);
-      std::vector<int> fill(n_tiles, 0);
       std::vector<int> ti_of(n_tiles), tj_of(n_tiles);
       for (int t = 0, ti = 0; ti < nt1; ++ti)
         for (int tj = 0; tj <= ti; ++tj, ++t) { ti_of[t] = ti; tj_of[t] = tj; }
+      auto tile_index = [](int ti, int tj) { return ti * (ti + 1) / 2 + tj; };
+      // a thin tile absorbed by a tall one has as many partial tiles as that tile has pieces
+      for (int t = 0; t < n_tiles; ++t)
+        out->tile_first[t + 1] = out->tile_first[t] + (absorbed[t] ? count[tile_index(tall_row, tj_of[t])] : count[t]);
+      out->tile_items.assign(out->tile_first[n_tiles], 0);
+      std::vector<int> fill(n_tiles, 0);
+      int n_slots = (int)pieces.size();  // slot of an item = its index; the second slots follow
       for (const Piece& pc : pieces) {  // sorted by lo: per tile the pieces arrive in ascending k order
-        out->tile_items[out->tile_first[pc.t] + fill[pc.t]++] = (int)out->items.size();
-        out->items.push_back({ti_of[pc.t], tj_of[pc.t], (int)pc.lo, (int)pc.hi});
+        const int item = (int)out->items.size();
+        out->tile_items[out->tile_first[pc.t] + fill[pc.t]++] = item;
+        int slot2 = -1;
+        if (is_tall[pc.t]) {
+          slot2 = n_slots++;
+          const int thin = tile_index(nt1 - 1, tj_of[pc.t]);
+          out->tile_items[out->tile_first[thin] + fill[thin]++] = slot2;
+        }
+        out->items.push_back({ti_of[pc.t], tj_of[pc.t], (int)pc.lo, (int)pc.hi, slot2});
       }
+      out->n_slots = n_slots;
+      out->tall_row = tall_row;
       out->makespan = makespan;
     }
     return makespan;
@@ -757,7 +845,7 @@ int syrk_plan_engine(ba_engine* e) {
   BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&e->syrk_items), plan.items.size() * sizeof(SyrkItem), (cudaStream_t)0));
   BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&e->syrk_tile_first), plan.tile_first.size() * sizeof(int), (cudaStream_t)0));
   BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&e->syrk_tile_items), plan.tile_items.size() * sizeof(int), (cudaStream_t)0));
-  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&e->Spart), plan.items.size() * tt * sizeof(double), (cudaStream_t)0));
+  BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&e->Spart), (size_t)plan.n_slots * tt * sizeof(double), (cudaStream_t)0));
   BA_CUDA(cudaMemcpy(e->syrk_items, plan.items.data(), plan.items.size() * sizeof(SyrkItem), cudaMemcpyHostToDevice));
   BA_CUDA(cudaMemcpy(e->syrk_tile_first, plan.tile_first.data(), plan.tile_first.size() * sizeof(int), cudaMemcpyHostToDevice));
   BA_CUDA(cudaMemcpy(e->syrk_tile_items, plan.tile_items.data(), plan.tile_items.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -788,14 +876,14 @@ static EncodeTiledFn tensor_map_encoder() {
   return fn;
 }
 
-// k-major operand `base` [rows][ld] doubles, `cols` valid columns: boxes of kTmaLds (132) columns x
-// kTmaKC rows (see syrk_tma_kernel for the four extra columns).
-static int make_operand_map(CUtensorMap* map, const double* base, int cols, int64_t rows, int ld) {
+// k-major operand `base` [rows][ld] doubles, `cols` valid columns: boxes of `box_cols` columns (kTmaLda
+// = 148 for the row operand, kTmaLdb = 132 for the column operand) x kTmaKC rows.
+static int make_operand_map(CUtensorMap* map, const double* base, int cols, int64_t rows, int ld, int box_cols) {
   EncodeTiledFn enc = tensor_map_encoder();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return BA_ERR_CUDA; }
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
-  const cuuint32_t box[2] = {(cuuint32_t)kTmaLds, (cuuint32_t)kTmaKC};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)kTmaKC};
   const cuuint32_t estride[2] = {1, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box,
                          estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -819,13 +907,14 @@ template <int TILE, int WR, int WC, int KC>
 static int launch_syrk(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
   const int64_t n_chunks = e->k_pad / KC;
   if (TILE == kTmaTile && KC == kTmaKC && syrk_use_tma()) {
-    CUtensorMap map;
-    BA_TRY(make_operand_map(&map, e->Yt, e->n_pad, e->k_pad, e->n_pad));
+    CUtensorMap mapA, mapB;
+    BA_TRY(make_operand_map(&mapA, e->Yt, e->n_pad, e->k_pad, e->n_pad, kTmaLda));
+    BA_TRY(make_operand_map(&mapB, e->Yt, e->n_pad, e->k_pad, e->n_pad, kTmaLdb));
     BA_CUDA(cudaFuncSetAttribute(syrk_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kTmaSmemBytes));
     ProfScope ps(e, PG_SYRK, s);
     syrk_tma_kernel<false><<<e->syrk_n_items, kTmaThreads, kTmaSmemBytes, s>>>(
-        map, e->n_pad, e->n_pad, n_chunks, e->syrk_items, e->Spart, ctl, 0, SubSplit{0, 1, 0, 0, {}});
+        mapA, mapB, e->n_pad, e->n_pad, n_chunks, e->syrk_items, e->Spart, ctl, 0, SubSplit{0, 1, 0, 0, {}});
     BA_LAUNCH_CHECK();
   } else {
     const size_t smem = (size_t)2 * kStages * KC * (TILE + 4) * sizeof(double);
@@ -872,11 +961,12 @@ static int launch_syrk_sub(double* S, int ld, int n_rows, int t0, const double* 
     for (int q = 0; q < split->world; ++q) sp.peer[q] = split->S_peer[q] + origin;
   }
   if (TILE == kTmaTile && KC == kTmaKC && syrk_use_tma()) {
-    CUtensorMap map;
-    BA_TRY(make_operand_map(&map, Lt + t0, n_valid, depth, ld));
+    CUtensorMap mapA, mapB;
+    BA_TRY(make_operand_map(&mapA, Lt + t0, n_valid, depth, ld, kTmaLda));
+    BA_TRY(make_operand_map(&mapB, Lt + t0, n_valid, depth, ld, kTmaLdb));
     BA_CUDA(cudaFuncSetAttribute(syrk_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kTmaSmemBytes));
-    syrk_tma_kernel<true><<<n_tiles, kTmaThreads, kTmaSmemBytes, s>>>(map, ld, n_valid, n_chunks, nullptr,
+    syrk_tma_kernel<true><<<n_tiles, kTmaThreads, kTmaSmemBytes, s>>>(mapA, mapB, ld, n_valid, n_chunks, nullptr,
                                                                       S + origin, ctl, n_store, sp);
     BA_LAUNCH_CHECK();
     return BA_OK;
@@ -967,8 +1057,26 @@ int syrk_plan_selftest(int n_cams, int64_t n_points, int tile, int num_sms, int*
   const int64_t n_chunks = k_pad / syrk_kc(tile);
   const int nt = (int)plan.tile_first.size() - 1;
   double work = 0.0;
+  const int nt1_all = (n_pad + tile - 1) / tile;
   for (int t = 0; t < nt; ++t) {
     int64_t pos = 0;
+    {
+      // a thin tile folded into the tall tile above it: as many second slots as that tile has pieces
+      int ti = 0;
+      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+      const int tj = t - ti * (ti + 1) / 2;
+      if (plan.tall_row >= 0 && ti == nt1_all - 1 && tj < plan.tall_row) {
+        const int tt = plan.tall_row * (plan.tall_row + 1) / 2 + tj;
+        const int cnt = plan.tile_first[t + 1] - plan.tile_first[t];
+        if (cnt != plan.tile_first[tt + 1] - plan.tile_first[tt]) { set_error("plan: thin tile %d has %d slots", t, cnt); return BA_ERR_STATE; }
+        for (int k = 0; k < cnt; ++k) {
+          const int slot = plan.tile_items[plan.tile_first[t] + k];
+          const SyrkItem& it = plan.items[plan.tile_items[plan.tile_first[tt] + k]];
+          if (slot < (int)plan.items.size() || slot >= plan.n_slots || it.slot2 != slot) { set_error("plan: thin tile %d slot %d", t, slot); return BA_ERR_STATE; }
+        }
+        continue;
+      }
+    }
     for (int k = plan.tile_first[t]; k < plan.tile_first[t + 1]; ++k) {
       const SyrkItem& it = plan.items[plan.tile_items[k]];
       int ti = 0;

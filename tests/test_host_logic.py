@@ -211,3 +211,31 @@ def test_schur_product_plan_covers_every_tile_once(n_cams, n_points, tile):
     assert ni.value >= nt.value
     if n_points >= 10_000:
         assert ideal.value / mk.value > 0.85
+
+
+@pytest.mark.parametrize("n_cams,n_points", [(200, 100_000), (200, 12_500), (50, 10_000), (114, 4_000), (320, 450)])
+def test_schur_product_plan_for_the_tma_kernel(n_cams, n_points):
+    """The same self-check with the planner told to plan for the TMA-fed kernel (the build container
+    has no driver, so the library would otherwise plan for the cp.async kernel): folded diagonal
+    tiles, and -- when at most 16 rows are left over (200 cameras: n_pad = 14 x 128 + 16) -- the ragged
+    last tile row folded into "tall" tiles of the row above, whose thin tiles then own no items but
+    one second partial-tile slot per piece of the tall tile."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, ctypes as C; sys.path.insert(0, %r); import ba_b200\n"
+        "cabi = ba_b200.submodule('_cabi'); lib = cabi.load()\n"
+        "ni, nt, mk, ideal = C.c_int(), C.c_int(), C.c_double(), C.c_double()\n"
+        "cabi.check(lib.ba_syrk_plan_info(%d, %d, 128, 148, C.byref(ni), C.byref(nt), C.byref(mk), C.byref(ideal)))\n"
+        "print(ni.value, nt.value, mk.value, ideal.value)\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                 n_cams, n_points)
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BA_SYRK_PLAN_ASSUME_TMA="1"),
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    ni, nt, mk, ideal = out.stdout.split()
+    n_pad = (9 * n_cams + 1 + 7) // 8 * 8
+    nt1 = (n_pad + 127) // 128
+    assert int(nt) == nt1 * (nt1 + 1) // 2 and int(ni) >= 1
+    if n_points >= 10_000:
+        assert float(ideal) / float(mk) > 0.85
