@@ -104,6 +104,8 @@ struct ba_engine {
   int n_full = 0, rhs_row = 0, n_pad = 0;
   int syrk_tile = 128;
   int syrk_n_items = 0, syrk_n_tiles = 0;
+  int syrk_n_ctas = 0;                 // CTAs of the SYRK launch (= items unless stream-K planned)
+  int* syrk_cta_first = nullptr;       // [syrk_n_ctas + 1] stream-K: first item of every CTA (else null)
   ba::SyrkItem* syrk_items = nullptr;  // [syrk_n_items] launch order
   int* syrk_tile_first = nullptr;      // [syrk_n_tiles + 1]
   int* syrk_tile_items = nullptr;      // items of each tile in ascending k order

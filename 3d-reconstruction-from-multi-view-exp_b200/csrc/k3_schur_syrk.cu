@@ -320,12 +320,12 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
       : "memory");
 }
 
-// Epilogue of one accumulator pair at tile-local (rl, cl), cl even: the partial tile of the item,
-// or (SUB) subtracted in place from the lower triangle of S, with the peer stores of a divided update.
+// Epilogue of one accumulator pair at tile-local (rl, cl), cl even: into the item's partial tile
+// (`part` points at it), or (SUB) subtracted in place from the lower triangle of S (`part`), with
+// the peer stores of a divided update.
 template <bool SUB>
 __device__ __forceinline__ void syrk_store_pair(double v0, double v1, int ti, int tj, int rl, int cl, int ld,
-                                                int n_store, double* __restrict__ part, const SubSplit& sp,
-                                                int slot = -1) {
+                                                int n_store, double* __restrict__ part, const SubSplit& sp) {
   constexpr int TILE = kTmaTile;
   if (SUB) {
     const int r = ti * TILE + rl, c = tj * TILE + cl;
@@ -349,37 +349,47 @@ __device__ __forceinline__ void syrk_store_pair(double v0, double v1, int ti, in
           if (q != sp.rank) sp.peer[q][off] = v;
     }
   } else {
-    // rows >= TILE of a tall item belong to the thin tile below: its own slot, rows from 0
-    const size_t s = slot >= 0 ? (size_t)slot : (size_t)blockIdx.x;
-    const int r = slot >= 0 ? rl - TILE : rl;
-    *reinterpret_cast<double2*>(part + s * TILE * TILE + (size_t)r * TILE + cl) = make_double2(v0, v1);
+    // `part` is the item's own partial tile
+    *reinterpret_cast<double2*>(part + (size_t)rl * TILE + cl) = make_double2(v0, v1);
   }
 }
 
+// One CTA runs a list of SEGMENTS (work items: tile x k-range), items[cta_first[b] .. cta_first[b + 1])
+// -- one item per CTA when cta_first is null (large operands: the planner cuts whole waves of items
+// in k-major order so that a k-slab stays in the L2), several for small operands (stream-K: every
+// CTA gets the same modelled work, crossing tile boundaries).  The TMA ring runs across segment
+// boundaries: the elected thread keeps its own cursor two to three chunks ahead of the warps, so the
+// pipeline is filled once per CTA, not once per item.  The slot of an item's partial tile is its
+// index in `items`.
 template <bool SUB>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 syrk_tma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, int ld,
-                int n_valid, int64_t n_chunks, const SyrkItem* __restrict__ items, double* __restrict__ part,
-                const ba_lm_state* ctl, int n_store, SubSplit sp) {
+                int n_valid, int64_t n_chunks, const SyrkItem* __restrict__ items, const int* __restrict__ cta_first,
+                double* __restrict__ part, const ba_lm_state* ctl, int n_store, SubSplit sp) {
   if (ctl && ctl->done) return;
   constexpr int TILE = kTmaTile, KC = kTmaKC, LDA = kTmaLda, LDB = kTmaLdb, WR = 4, WC = 4;
   constexpr int WM = TILE / WR, WN = TILE / WC, FM = WM / 8, FN = WN / 8;
   extern __shared__ unsigned char smem_raw[];
 
-  int ti, tj, slot2 = -1;
-  int64_t c_lo, c_hi;
+  int seg_lo = blockIdx.x, seg_hi = blockIdx.x + 1;
+  if (!SUB && cta_first) { seg_lo = cta_first[blockIdx.x]; seg_hi = cta_first[blockIdx.x + 1]; }
+  // segment `seg` -> tile, first chunk, chunks, second slot
+  auto segment = [&](int seg, int& ti, int& tj, int& c_lo, int& nk, int& slot2) {
+    if (SUB) {
+      tile_from_linear(seg, ti, tj);
+      c_lo = 0;
+      nk = (int)n_chunks;
+      slot2 = -1;
+    } else {
+      const SyrkItem it = items[seg];
+      ti = it.ti; tj = it.tj; c_lo = it.c_lo; nk = it.c_hi > it.c_lo ? it.c_hi - it.c_lo : 0; slot2 = it.slot2;
+    }
+  };
   if (SUB) {
+    int ti, tj;
     tile_from_linear(blockIdx.x, ti, tj);
     if (sp.world > 1 && (sp.tile_row0 + ti) % sp.world != sp.rank) return;  // another rank's tile row
-    c_lo = 0;
-    c_hi = n_chunks;
-  } else {
-    const SyrkItem it = items[blockIdx.x];
-    ti = it.ti; tj = it.tj; c_lo = it.c_lo; c_hi = it.c_hi; slot2 = it.slot2;
   }
-  const bool diag = ti == tj;
-  const bool tall = slot2 >= 0;
-  const int nk = (int)(c_hi > c_lo ? c_hi - c_lo : 0);
 
   // carve shared memory: operand stages (128-byte aligned for the TMA unit), then the mbarriers
   const unsigned base = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -388,15 +398,28 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   const unsigned bars = base + kTmaStages * kTmaStageBytes;
   auto full_bar = [&](int st) { return bars + 8u * st; };
   auto empty_bar = [&](int st) { return bars + 8u * (kTmaStages + st); };
-  const unsigned stage_bytes = kTmaABytes + (diag ? 0u : kTmaBBytes);
-  // chunk `kc` of this item into stage kc % kTmaStages (one elected thread)
-  auto issue = [&](int kc) {
-    const int st = kc % kTmaStages;
+
+  // ---- the elected thread's side of the ring: a cursor over the chunks of all segments ----------
+  int pseg = seg_lo, pkc = 0;   // next chunk to issue
+  unsigned issued = 0;          // chunks issued so far = global index of the next one
+  auto issue_next = [&]() {     // thread 0 only
+    int ti, tj, c_lo, nk, slot2;
+    while (pseg < seg_hi) {
+      segment(pseg, ti, tj, c_lo, nk, slot2);
+      if (pkc < nk) break;
+      ++pseg;
+      pkc = 0;
+    }
+    if (pseg >= seg_hi) return;
+    const int st = (int)(issued % kTmaStages);
     const unsigned dst = base + (unsigned)st * kTmaStageBytes;
-    const int row = (int)((c_lo + kc) * KC);
-    mbar_arrive_expect_tx(full_bar(st), stage_bytes);
+    const int row = (c_lo + pkc) * KC;
+    const bool dg = ti == tj;
+    mbar_arrive_expect_tx(full_bar(st), kTmaABytes + (dg ? 0u : kTmaBBytes));
     tma_load_2d(dst, &tmapA, ti * TILE, row, full_bar(st));
-    if (!diag) tma_load_2d(dst + kTmaABytes, &tmapB, tj * TILE, row, full_bar(st));
+    if (!dg) tma_load_2d(dst + kTmaABytes, &tmapB, tj * TILE, row, full_bar(st));
+    ++issued;
+    ++pkc;
   };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -406,176 +429,185 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       mbar_init(empty_bar(st), kTmaThreads / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int kc = 0; kc < kTmaStages && kc < nk; ++kc) issue(kc);
+    for (int k = 0; k < kTmaStages; ++k) issue_next();
   }
   __syncthreads();
-  // Before chunk kc is computed the elected thread refills the stage of chunk kc - 1 with chunk
-  // kc + 2 (every warp is done with chunk kc - 1 or about to be: the wait on `empty` is short).
-  auto refill = [&](int kc) {
+  // Before global chunk g is computed the elected thread refills the stage of chunk g - 1 with the
+  // next chunk not yet issued (every warp is done with chunk g - 1 or about to be: the wait on
+  // `empty` is short).
+  auto refill = [&](unsigned g) {
     if (warp == 0) {
-      if (lane == 0 && kc >= 1 && kc + kTmaStages - 1 < nk) {
-        mbar_wait(empty_bar((kc - 1) % kTmaStages), (unsigned)((kc - 1) / kTmaStages) & 1u);
-        issue(kc + kTmaStages - 1);
+      if (lane == 0 && g >= 1 && issued == g + kTmaStages - 1) {
+        mbar_wait(empty_bar((int)((g - 1) % kTmaStages)), ((g - 1) / kTmaStages) & 1u);
+        issue_next();
       }
       __syncwarp();
     }
   };
   const int kq = lane & 3;
+  unsigned g = 0;  // global chunk counter of this CTA
 
-  if (diag) {
-    // Diagonal tile: only the 136 fragments (8 x 8) on or below the diagonal of the 16 x 16 fragment
-    // grid are needed.  Fragment rows r and 15 - r together hold 17 of them; the pair is shared by
-    // two warps, one taking nine fragments (row 15 - r, columns 0..8), the other eight (the rest of
-    // row 15 - r and all of row r); which warp of a pair takes nine alternates so that every
-    // scheduler partition (warp % 4) carries 34 fragments per k-step.
-    const int pr = warp >> 1;
-    const bool nine = (((warp & 1) ^ ((warp >> 2) & 1)) == 0);
-    const int r_hi = 15 - pr, r_lo = pr;
-    const int n_hi = nine ? 9 : 7 - pr;        // fragments this warp takes from row r_hi
-    const int c_hi0 = nine ? 0 : 9;            // ... starting at this column
-    const int nfr = nine ? 9 : 8;
-    const int frag_rows_valid = (n_valid - ti * TILE + 7) / 8;  // ragged last tile
-    int boffj[9];
-    bool usej[9];
-    bool any = false;
+  for (int seg = seg_lo; seg < seg_hi; ++seg) {
+    int ti, tj, c_lo_unused, nk, slot2;
+    segment(seg, ti, tj, c_lo_unused, nk, slot2);
+    const bool diag = ti == tj;
+    const bool tall = slot2 >= 0;
+    double* const slot_part = SUB ? part : part + (size_t)seg * TILE * TILE;
+
+    if (diag) {
+      // Diagonal tile: only the 136 fragments (8 x 8) on or below the diagonal of the 16 x 16
+      // fragment grid are needed.  Fragment rows r and 15 - r together hold 17 of them; the pair is
+      // shared by two warps, one taking nine fragments (row 15 - r, columns 0..8), the other eight
+      // (the rest of row 15 - r and all of row r); which warp of a pair takes nine alternates so
+      // that every scheduler partition (warp % 4) carries 34 fragments per k-step.
+      const int pr = warp >> 1;
+      const bool nine = (((warp & 1) ^ ((warp >> 2) & 1)) == 0);
+      const int r_hi = 15 - pr, r_lo = pr;
+      const int n_hi = nine ? 9 : 7 - pr;        // fragments this warp takes from row r_hi
+      const int c_hi0 = nine ? 0 : 9;            // ... starting at this column
+      const int nfr = nine ? 9 : 8;
+      const int frag_rows_valid = (n_valid - ti * TILE + 7) / 8;  // ragged last tile
+      int boffj[9];
+      bool usej[9];
+      bool any = false;
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      const bool hi = j < n_hi;
-      const int rf = hi ? r_hi : r_lo;
-      const int cf = hi ? c_hi0 + j : j - n_hi;
-      usej[j] = j < nfr && rf < frag_rows_valid;
-      any |= usej[j];
-      boffj[j] = kq * LDA + 8 * cf + (lane >> 2);
+      for (int j = 0; j < 9; ++j) {
+        const bool hi = j < n_hi;
+        const int rf = hi ? r_hi : r_lo;
+        const int cf = hi ? c_hi0 + j : j - n_hi;
+        usej[j] = j < nfr && rf < frag_rows_valid;
+        any |= usej[j];
+        boffj[j] = kq * LDA + 8 * cf + (lane >> 2);
+      }
+      const int aoff_hi = kq * LDA + 8 * r_hi + (lane >> 2);
+      const int aoff_lo = kq * LDA + 8 * r_lo + (lane >> 2);
+      double dacc[9][2];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) dacc[j][0] = dacc[j][1] = 0.0;
+      for (int kc = 0; kc < nk; ++kc, ++g) {
+        refill(g);
+        const int st = (int)(g % kTmaStages);
+        mbar_wait(full_bar(st), (g / kTmaStages) & 1u);
+        const double* a = stages + (size_t)st * kStageDoubles;
+        if (any) {
+#pragma unroll
+          for (int kk = 0; kk < KC; kk += 4) {
+            const double fa_hi = a[aoff_hi + kk * LDA], fa_lo = a[aoff_lo + kk * LDA];
+            double fb[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) fb[j] = a[boffj[j] + kk * LDA];
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+              if (usej[j]) dmma884(dacc[j][0], dacc[j][1], j < n_hi ? fa_hi : fa_lo, fb[j]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar(st));
+      }
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        if (!usej[j]) continue;
+        const bool hi = j < n_hi;
+        syrk_store_pair<SUB>(dacc[j][0], dacc[j][1], ti, ti, 8 * (hi ? r_hi : r_lo) + (lane >> 2),
+                             8 * (hi ? c_hi0 + j : j - n_hi) + 2 * (lane & 3), ld, n_store, slot_part, sp);
+      }
+      continue;
     }
-    const int aoff_hi = kq * LDA + 8 * r_hi + (lane >> 2);
-    const int aoff_lo = kq * LDA + 8 * r_lo + (lane >> 2);
-    double dacc[9][2];
+
+    // (A column-per-warp mapping for the thin tiles of a ragged last tile row was tried and dropped:
+    // with only 2 of 16 fragment rows to compute, the warps outrun the three-stage TMA ring and wait
+    // for every chunk -- C3 went from 28.8 to 31.1 ms.  Such rows are folded into tall tiles instead.)
+    const int wr = warp / WC, wc = warp % WC;
+    int vm = 0, vn = 0;
 #pragma unroll
-    for (int j = 0; j < 9; ++j) dacc[j][0] = dacc[j][1] = 0.0;
-    for (int kc = 0; kc < nk; ++kc) {
-      refill(kc);
-      const int st = kc % kTmaStages;
-      mbar_wait(full_bar(st), (unsigned)(kc / kTmaStages) & 1u);
-      const double* a = stages + (size_t)st * kStageDoubles;
-      if (any) {
+    for (int i = 0; i < FM; ++i) vm += (ti * TILE + wr * WM + 8 * i) < n_valid;
+#pragma unroll
+    for (int j = 0; j < FN; ++j) vn += (tj * TILE + wc * WN + 8 * j) < n_valid;
+    const bool full = vm == FM && vn == FN;
+    const int aoff = kq * LDA + wr * WM + (lane >> 2);
+    const int boff = kq * LDB + wc * WN + (lane >> 2);
+    // tall item: this warp's two extra fragments -- fragment row 16 + (wr & 1) of A against its B
+    // fragments 2 (wr >> 1) and 2 (wr >> 1) + 1
+    const int xoff = kq * LDA + TILE + 8 * (wr & 1) + (lane >> 2);
+    const int xj = 2 * (wr >> 1);
+    const bool xvalid = tall && (ti + 1) * TILE + 8 * (wr & 1) < n_valid;
+
+    double acc[FM][FN][2], xacc[2][2];
+#pragma unroll
+    for (int i = 0; i < FM; ++i)
+#pragma unroll
+      for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    xacc[0][0] = xacc[0][1] = xacc[1][0] = xacc[1][1] = 0.0;
+
+    for (int kc = 0; kc < nk; ++kc, ++g) {
+      refill(g);
+      const int st = (int)(g % kTmaStages);
+      mbar_wait(full_bar(st), (g / kTmaStages) & 1u);
+      const double* a = stages + (size_t)st * kStageDoubles + aoff;
+      const double* b = stages + (size_t)st * kStageDoubles + kTmaADoubles + boff;
+      if (full && xvalid) {
+        const double* x = stages + (size_t)st * kStageDoubles + xoff;
 #pragma unroll
         for (int kk = 0; kk < KC; kk += 4) {
-          const double fa_hi = a[aoff_hi + kk * LDA], fa_lo = a[aoff_lo + kk * LDA];
-          double fb[9];
+          double fa[FM], fb[FN];
 #pragma unroll
-          for (int j = 0; j < 9; ++j) fb[j] = a[boffj[j] + kk * LDA];
+          for (int i = 0; i < FM; ++i) fa[i] = a[kk * LDA + 8 * i];
 #pragma unroll
-          for (int j = 0; j < 9; ++j)
-            if (usej[j]) dmma884(dacc[j][0], dacc[j][1], j < n_hi ? fa_hi : fa_lo, fb[j]);
+          for (int j = 0; j < FN; ++j) fb[j] = b[kk * LDB + 8 * j];
+          const double fx = x[kk * LDA];
+#pragma unroll
+          for (int i = 0; i < FM; ++i)
+#pragma unroll
+            for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+          dmma884(xacc[0][0], xacc[0][1], fx, xj == 0 ? fb[0] : fb[2]);
+          dmma884(xacc[1][0], xacc[1][1], fx, xj == 0 ? fb[1] : fb[3]);
+        }
+      } else if (full) {
+#pragma unroll
+        for (int kk = 0; kk < KC; kk += 4) {
+          double fa[FM], fb[FN];
+#pragma unroll
+          for (int i = 0; i < FM; ++i) fa[i] = a[kk * LDA + 8 * i];
+#pragma unroll
+          for (int j = 0; j < FN; ++j) fb[j] = b[kk * LDB + 8 * j];
+#pragma unroll
+          for (int i = 0; i < FM; ++i)
+#pragma unroll
+            for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
+        }
+      } else if (vm > 0 && vn > 0) {
+#pragma unroll
+        for (int kk = 0; kk < KC; kk += 4) {
+          double fa[FM], fb[FN];
+#pragma unroll
+          for (int i = 0; i < FM; ++i) fa[i] = a[kk * LDA + 8 * i];
+#pragma unroll
+          for (int j = 0; j < FN; ++j) fb[j] = b[kk * LDB + 8 * j];
+#pragma unroll
+          for (int i = 0; i < FM; ++i)
+#pragma unroll
+            for (int j = 0; j < FN; ++j)
+              if (i < vm && j < vn) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar(st));
+      if (lane == 0) mbar_arrive(empty_bar(st));  // this warp has read the stage
     }
+
+    const int orow = wr * WM + (lane >> 2);
+    const int ocol = wc * WN + 2 * (lane & 3);
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      if (!usej[j]) continue;
-      const bool hi = j < n_hi;
-      syrk_store_pair<SUB>(dacc[j][0], dacc[j][1], ti, ti, 8 * (hi ? r_hi : r_lo) + (lane >> 2),
-                           8 * (hi ? c_hi0 + j : j - n_hi) + 2 * (lane & 3), ld, n_store, part, sp);
+    for (int i = 0; i < FM; ++i)
+#pragma unroll
+      for (int j = 0; j < FN; ++j)
+        syrk_store_pair<SUB>(acc[i][j][0], acc[i][j][1], ti, tj, orow + 8 * i, ocol + 8 * j, ld, n_store, slot_part, sp);
+    if (xvalid) {
+      // the ragged rows below the tile: rows 0.. of the thin tile's partial slot (never with SUB)
+      double* xp = part + (size_t)slot2 * TILE * TILE + (size_t)(8 * (wr & 1) + (lane >> 2)) * TILE;
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        *reinterpret_cast<double2*>(xp + wc * WN + 8 * (xj + e) + 2 * (lane & 3)) = make_double2(xacc[e][0], xacc[e][1]);
     }
-    return;
-  }
-
-  // (A column-per-warp mapping for the thin tiles of a ragged last tile row was tried and dropped:
-  // with only 2 of 16 fragment rows to compute, the warps outrun the three-stage TMA ring and wait
-  // for every chunk -- C3 went from 28.8 to 31.1 ms.  The square mapping below leaves such a tile at
-  // 0.34 of a full tile's time for 0.125 of its work.)
-  const int wr = warp / WC, wc = warp % WC;
-  int vm = 0, vn = 0;
-#pragma unroll
-  for (int i = 0; i < FM; ++i) vm += (ti * TILE + wr * WM + 8 * i) < n_valid;
-#pragma unroll
-  for (int j = 0; j < FN; ++j) vn += (tj * TILE + wc * WN + 8 * j) < n_valid;
-  const bool full = vm == FM && vn == FN;
-  const int aoff = kq * LDA + wr * WM + (lane >> 2);
-  const int boff = kq * LDB + wc * WN + (lane >> 2);
-  // tall item: this warp's two extra fragments -- fragment row 16 + (wr & 1) of A against its B
-  // fragments 2 (wr >> 1) and 2 (wr >> 1) + 1
-  const int xoff = kq * LDA + TILE + 8 * (wr & 1) + (lane >> 2);
-  const int xj = 2 * (wr >> 1);
-  const bool xvalid = tall && (ti + 1) * TILE + 8 * (wr & 1) < n_valid;
-
-  double acc[FM][FN][2], xacc[2][2];
-#pragma unroll
-  for (int i = 0; i < FM; ++i)
-#pragma unroll
-    for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  xacc[0][0] = xacc[0][1] = xacc[1][0] = xacc[1][1] = 0.0;
-
-  for (int kc = 0; kc < nk; ++kc) {
-    refill(kc);
-    const int st = kc % kTmaStages;
-    mbar_wait(full_bar(st), (unsigned)(kc / kTmaStages) & 1u);
-    const double* a = stages + (size_t)st * kStageDoubles + aoff;
-    const double* b = stages + (size_t)st * kStageDoubles + kTmaADoubles + boff;
-    if (full && xvalid) {
-      const double* x = stages + (size_t)st * kStageDoubles + xoff;
-#pragma unroll
-      for (int kk = 0; kk < KC; kk += 4) {
-        double fa[FM], fb[FN];
-#pragma unroll
-        for (int i = 0; i < FM; ++i) fa[i] = a[kk * LDA + 8 * i];
-#pragma unroll
-        for (int j = 0; j < FN; ++j) fb[j] = b[kk * LDB + 8 * j];
-        const double fx = x[kk * LDA];
-#pragma unroll
-        for (int i = 0; i < FM; ++i)
-#pragma unroll
-          for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-        dmma884(xacc[0][0], xacc[0][1], fx, xj == 0 ? fb[0] : fb[2]);
-        dmma884(xacc[1][0], xacc[1][1], fx, xj == 0 ? fb[1] : fb[3]);
-      }
-    } else if (full) {
-#pragma unroll
-      for (int kk = 0; kk < KC; kk += 4) {
-        double fa[FM], fb[FN];
-#pragma unroll
-        for (int i = 0; i < FM; ++i) fa[i] = a[kk * LDA + 8 * i];
-#pragma unroll
-        for (int j = 0; j < FN; ++j) fb[j] = b[kk * LDB + 8 * j];
-#pragma unroll
-        for (int i = 0; i < FM; ++i)
-#pragma unroll
-          for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-      }
-    } else if (vm > 0 && vn > 0) {
-#pragma unroll
-      for (int kk = 0; kk < KC; kk += 4) {
-        double fa[FM], fb[FN];
-#pragma unroll
-        for (int i = 0; i < FM; ++i) fa[i] = a[kk * LDA + 8 * i];
-#pragma unroll
-        for (int j = 0; j < FN; ++j) fb[j] = b[kk * LDB + 8 * j];
-#pragma unroll
-        for (int i = 0; i < FM; ++i)
-#pragma unroll
-          for (int j = 0; j < FN; ++j)
-            if (i < vm && j < vn) dmma884(acc[i][j][0], acc[i][j][1], fa[i], fb[j]);
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty_bar(st));  // this warp has read the stage
-  }
-
-  const int orow = wr * WM + (lane >> 2);
-  const int ocol = wc * WN + 2 * (lane & 3);
-#pragma unroll
-  for (int i = 0; i < FM; ++i)
-#pragma unroll
-    for (int j = 0; j < FN; ++j)
-      syrk_store_pair<SUB>(acc[i][j][0], acc[i][j][1], ti, tj, orow + 8 * i, ocol + 8 * j, ld, n_store, part, sp);
-  if (xvalid) {
-    const int xr = TILE + 8 * (wr & 1) + (lane >> 2);
-#pragma unroll
-    for (int e = 0; e < 2; ++e)
-      syrk_store_pair<SUB>(xacc[e][0], xacc[e][1], ti, tj, xr, wc * WN + 8 * (xj + e) + 2 * (lane & 3), ld, n_store,
-                           part, sp, slot2);
   }
 }
 
@@ -701,6 +733,7 @@ struct SyrkPlan {
   std::vector<SyrkItem> items;       // launch order: ascending k range, then tile
   std::vector<int> tile_first;       // [n_tiles + 1]
   std::vector<int> tile_items;       // partial-tile slot per (tile, piece), pieces in ascending k order
+  std::vector<int> cta_first;        // stream-K plans: [n_ctas + 1] first item of every CTA (else empty)
   int n_slots = 0;                   // partial tiles: one per item + one per tall item (its thin tile below)
   int tall_row = -1;                 // tile row whose off-diagonal tiles also compute the ragged rows below
   double makespan = 0.0;             // modelled duration in k-rows of a full tile on one SM slot
@@ -818,6 +851,71 @@ static SyrkPlan plan_syrk(int n_pad, int TILE, int WR, int WC, int64_t k_pad, in
   return plan;
 }
 
+// Small operands (the whole of Y^T stays in the 126 MB L2, so the order in which k-ranges are
+// visited does not matter): stream-K.  With whole items the C2 product is two waves of ~1000-row
+// items on 148 SMs -- the schedule, not the kernel, bounds it at 0.55 of the DMMA peak.  Here the
+// modelled work (tile weight x chunks, tile by tile) is dealt to one CTA per SM in equal shares,
+// crossing tile boundaries; a CTA's segments run through one TMA ring (syrk_tma_kernel), so the
+// pipeline is filled once per CTA.  Every segment still writes its own partial tile, and the tiles
+// are summed in ascending k order as before: deterministic.
+static SyrkPlan plan_streamk(int n_pad, int64_t k_pad, int num_sms) {
+  constexpr int TILE = kTmaTile, KC = kTmaKC;
+  const int nt1 = (n_pad + TILE - 1) / TILE;
+  const int n_tiles = nt1 * (nt1 + 1) / 2;
+  const int64_t n_chunks = k_pad / KC;
+  std::vector<double> w(n_tiles);
+  for (int t = 0, ti = 0; ti < nt1; ++ti)
+    for (int tj = 0; tj <= ti; ++tj, ++t) {
+      // executed 8 x 8 fragments per k-step against the 256 of a full tile; a thin tile is bound by
+      // the ring's latency instead (measured ~0.3)
+      const int rows = std::min(16, (n_pad - ti * TILE + 7) / 8);
+      const double frags = ti == tj ? rows * (rows + 1) / 2.0 : rows * 16.0;
+      w[t] = std::max(0.3, frags / 256.0);
+    }
+  const int64_t min_seg = 4;       // chunks
+  const double seg_cost = 1.5;     // chunks of a full tile: accumulator hand-over and the partial-tile store
+  double total = 0.0;
+  for (int t = 0; t < n_tiles; ++t) total += w[t] * (double)n_chunks + seg_cost;
+  const int G = num_sms;
+  const double budget = total / G + seg_cost;
+  SyrkPlan plan;
+  plan.tile_first.assign(n_tiles + 1, 0);
+  plan.cta_first.assign(1, 0);
+  int cta = 0;
+  double left = budget;
+  auto next_cta = [&]() {
+    plan.cta_first.push_back((int)plan.items.size());
+    ++cta;
+    left = budget;
+  };
+  for (int t = 0, ti = 0; ti < nt1; ++ti)
+    for (int tj = 0; tj <= ti; ++tj, ++t) {
+      int64_t pos = 0;
+      while (pos < n_chunks) {
+        const int64_t rem = n_chunks - pos;
+        int64_t can = (int64_t)std::floor((left - seg_cost) / w[t]);
+        if (cta == G - 1) can = rem;  // the last CTA takes whatever is left
+        if (can < min_seg && cta < G - 1) { next_cta(); continue; }
+        int64_t take = std::min<int64_t>(rem, std::max<int64_t>(can, min_seg));
+        if (rem - take < min_seg) take = rem;  // no crumbs
+        plan.tile_items.push_back((int)plan.items.size());
+        plan.items.push_back({ti, tj, (int)pos, (int)(pos + take), -1});
+        pos += take;
+        left -= (double)take * w[t] + seg_cost;
+      }
+      plan.tile_first[t + 1] = (int)plan.items.size();
+    }
+  while ((int)plan.cta_first.size() < G + 1) plan.cta_first.push_back((int)plan.items.size());
+  plan.n_slots = (int)plan.items.size();
+  plan.makespan = budget * KC;
+  return plan;
+}
+
+static bool use_streamk(int n_pad, int tile, int64_t k_pad) {
+  static const bool off = std::getenv("BA_SYRK_NO_STREAMK") != nullptr;  // A/B timing only
+  return !off && tile == kTmaTile && plan_for_tma() && (double)k_pad * n_pad * 8.0 <= 128.0 * 1024 * 1024;
+}
+
 // Plans are kept for the life of the process: the schedule search costs milliseconds of host
 // time, more than a small adjustment, and callers adjust scene after scene of the same shape.
 static const SyrkPlan& cached_plan(int n_pad, int tile, int64_t k_pad, int num_sms) {
@@ -828,8 +926,9 @@ static const SyrkPlan& cached_plan(int n_pad, int tile, int64_t k_pad, int num_s
   for (auto& kv : cache)
     if (kv.first.n_pad == n_pad && kv.first.tile == tile && kv.first.k_pad == k_pad && kv.first.sms == num_sms)
       return *kv.second;
-  SyrkPlan* p = new SyrkPlan(tile == 128 ? plan_syrk(n_pad, 128, 4, 4, k_pad, num_sms)
-                                         : plan_syrk(n_pad, 64, 2, 2, k_pad, num_sms));
+  SyrkPlan* p = new SyrkPlan(use_streamk(n_pad, tile, k_pad) ? plan_streamk(n_pad, k_pad, num_sms)
+                             : tile == 128 ? plan_syrk(n_pad, 128, 4, 4, k_pad, num_sms)
+                                           : plan_syrk(n_pad, 64, 2, 2, k_pad, num_sms));
   cache.push_back({Key{n_pad, tile, k_pad, num_sms}, p});
   return *p;
 }
@@ -839,6 +938,11 @@ int syrk_plan_engine(ba_engine* e) {
   if (!e->dense) return BA_OK;
   const SyrkPlan& plan = cached_plan(e->n_pad, e->syrk_tile, e->k_pad, e->num_sms);
   e->syrk_n_items = (int)plan.items.size();
+  e->syrk_n_ctas = plan.cta_first.empty() ? e->syrk_n_items : (int)plan.cta_first.size() - 1;
+  if (!plan.cta_first.empty()) {
+    BA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&e->syrk_cta_first), plan.cta_first.size() * sizeof(int), (cudaStream_t)0));
+    BA_CUDA(cudaMemcpy(e->syrk_cta_first, plan.cta_first.data(), plan.cta_first.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
   const int nt1 = (e->n_pad + e->syrk_tile - 1) / e->syrk_tile;
   e->syrk_n_tiles = nt1 * (nt1 + 1) / 2;
   const size_t tt = (size_t)e->syrk_tile * e->syrk_tile;
@@ -913,8 +1017,9 @@ static int launch_syrk(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
     BA_CUDA(cudaFuncSetAttribute(syrk_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kTmaSmemBytes));
     ProfScope ps(e, PG_SYRK, s);
-    syrk_tma_kernel<false><<<e->syrk_n_items, kTmaThreads, kTmaSmemBytes, s>>>(
-        mapA, mapB, e->n_pad, e->n_pad, n_chunks, e->syrk_items, e->Spart, ctl, 0, SubSplit{0, 1, 0, 0, {}});
+    syrk_tma_kernel<false><<<e->syrk_n_ctas, kTmaThreads, kTmaSmemBytes, s>>>(
+        mapA, mapB, e->n_pad, e->n_pad, n_chunks, e->syrk_items, e->syrk_cta_first, e->Spart, ctl, 0,
+        SubSplit{0, 1, 0, 0, {}});
     BA_LAUNCH_CHECK();
   } else {
     const size_t smem = (size_t)2 * kStages * KC * (TILE + 4) * sizeof(double);
@@ -967,7 +1072,7 @@ static int launch_syrk_sub(double* S, int ld, int n_rows, int t0, const double* 
     BA_CUDA(cudaFuncSetAttribute(syrk_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kTmaSmemBytes));
     syrk_tma_kernel<true><<<n_tiles, kTmaThreads, kTmaSmemBytes, s>>>(mapA, mapB, ld, n_valid, n_chunks, nullptr,
-                                                                      S + origin, ctl, n_store, sp);
+                                                                      nullptr, S + origin, ctl, n_store, sp);
     BA_LAUNCH_CHECK();
     return BA_OK;
   }
