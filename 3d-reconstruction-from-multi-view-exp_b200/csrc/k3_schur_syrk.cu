@@ -400,24 +400,24 @@ syrk_tma_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   auto empty_bar = [&](int st) { return bars + 8u * (kTmaStages + st); };
 
   // ---- the elected thread's side of the ring: a cursor over the chunks of all segments ----------
-  int pseg = seg_lo, pkc = 0;   // next chunk to issue
-  unsigned issued = 0;          // chunks issued so far = global index of the next one
-  auto issue_next = [&]() {     // thread 0 only
-    int ti, tj, c_lo, nk, slot2;
-    while (pseg < seg_hi) {
-      segment(pseg, ti, tj, c_lo, nk, slot2);
-      if (pkc < nk) break;
-      ++pseg;
+  int pseg = seg_lo - 1, pkc = 0, pnk = 0;   // cursor: segment, next chunk in it, its chunk count
+  int pti = 0, ptj = 0, pclo = 0;            // ... and its tile / first chunk (kept in registers:
+                                             // the item is read from global memory once per segment)
+  unsigned issued = 0;                       // chunks issued so far = global index of the next one
+  auto issue_next = [&]() {                  // thread 0 only
+    while (pkc >= pnk) {
+      if (++pseg >= seg_hi) { pseg = seg_hi; return; }
+      int slot2;
+      segment(pseg, pti, ptj, pclo, pnk, slot2);
       pkc = 0;
     }
-    if (pseg >= seg_hi) return;
     const int st = (int)(issued % kTmaStages);
     const unsigned dst = base + (unsigned)st * kTmaStageBytes;
-    const int row = (c_lo + pkc) * KC;
-    const bool dg = ti == tj;
+    const int row = (pclo + pkc) * KC;
+    const bool dg = pti == ptj;
     mbar_arrive_expect_tx(full_bar(st), kTmaABytes + (dg ? 0u : kTmaBBytes));
-    tma_load_2d(dst, &tmapA, ti * TILE, row, full_bar(st));
-    if (!dg) tma_load_2d(dst + kTmaABytes, &tmapB, tj * TILE, row, full_bar(st));
+    tma_load_2d(dst, &tmapA, pti * TILE, row, full_bar(st));
+    if (!dg) tma_load_2d(dst + kTmaABytes, &tmapB, ptj * TILE, row, full_bar(st));
     ++issued;
     ++pkc;
   };
@@ -911,9 +911,13 @@ static SyrkPlan plan_streamk(int n_pad, int64_t k_pad, int num_sms) {
   return plan;
 }
 
+// Measured on B200 (C2, 50 cameras x 10k points): 0.82 ms against 0.29 ms with whole items in k-major
+// order -- with every CTA streaming its own (tile, k-range) nothing is shared between the SMs any
+// more and the thin tiles' long k-ranges become the makespan.  The plan and the multi-segment kernel
+// are kept behind BA_SYRK_STREAMK=1 for the next attempt (k-major dealing of equal shares).
 static bool use_streamk(int n_pad, int tile, int64_t k_pad) {
-  static const bool off = std::getenv("BA_SYRK_NO_STREAMK") != nullptr;  // A/B timing only
-  return !off && tile == kTmaTile && plan_for_tma() && (double)k_pad * n_pad * 8.0 <= 128.0 * 1024 * 1024;
+  static const bool on = std::getenv("BA_SYRK_STREAMK") != nullptr;
+  return on && tile == kTmaTile && plan_for_tma() && (double)k_pad * n_pad * 8.0 <= 128.0 * 1024 * 1024;
 }
 
 // Plans are kept for the life of the process: the schedule search costs milliseconds of host
