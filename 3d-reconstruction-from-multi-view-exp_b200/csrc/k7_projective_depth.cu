@@ -522,6 +522,33 @@ pad_rows_kernel(int64_t N, int n, int ld, const double* __restrict__ W, double* 
     for (int a = lane; a < ld; a += 32) Wk[(size_t)j * ld + a] = a < n ? W[(size_t)j * n + a] : 0.0;
 }
 
+// Affine path (reference lib/affine_camera_calibration.py:224-240, _get_observation_matrix): the
+// observation matrix is centred per row of W = per column of the k-major array.  Per-warp partial
+// column sums in a fixed order (colsum_finish_kernel adds them), then the copy subtracts the means.
+__global__ void __launch_bounds__(256)
+col_partial_kernel(int64_t N, int n, const double* __restrict__ W, double* __restrict__ part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = warp_global(), nw = warps_total();
+  for (int a = lane; a < n; a += 32) {
+    double acc = 0.0;
+    for (int64_t j = w; j < N; j += nw) acc += W[(size_t)j * n + a];
+    part[(size_t)w * n + a] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pad_rows_centred_kernel(int64_t N, int n, int ld, const double* __restrict__ W, const double* __restrict__ colsum,
+                        double* __restrict__ mean, double* __restrict__ Wk) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = warps_total();
+  const double inv = 1.0 / (double)N;
+  if (blockIdx.x == 0)
+    for (int a = threadIdx.x; a < n; a += blockDim.x) mean[a] = colsum[a] * inv;
+  for (int64_t j = warp_global(); j < N; j += nw)
+    for (int a = lane; a < ld; a += 32)
+      Wk[(size_t)j * ld + a] = a < n ? W[(size_t)j * n + a] - colsum[a] * inv : 0.0;
+}
+
 // Cyclic Jacobi on a symmetric K x K matrix held by ONE thread (K <= 12): eigenvalues on the
 // diagonal of a, eigenvectors in the columns of e.
 template <int K>
@@ -1036,8 +1063,9 @@ extern "C" int ba_depth_dual_probe(double* V4, double* R60, double* W12, double*
   return BA_OK;
 }
 
-extern "C" int ba_factorize_rank4(int device, int64_t n_cols, int32_t n_rows, const double* Wt, double* M_out,
-                                  double* S_out, double* sigma_out, int mem, void* stream) {
+static int factorize_rank4_impl(int device, int64_t n_cols, int32_t n_rows, const double* Wt, bool centre,
+                                double* mean_out, double* M_out, double* S_out, double* sigma_out, int mem,
+                                void* stream) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_error("no CUDA device: the factorisation has no CPU path");
@@ -1080,7 +1108,22 @@ extern "C" int ba_factorize_rank4(int device, int64_t n_cols, int32_t n_rows, co
   BA_CUDA(cudaMemsetAsync(Wk, 0, (size_t)k_pad * ld * d, s));
   BA_CUDA(cudaMemsetAsync(P, 0, (size_t)ld * ld * d, s));
   BA_CUDA(cudaMemsetAsync(status, 0, sizeof(int), s));
-  pad_rows_kernel<<<grid, 256, 0, s>>>(N, n, ld, dW, Wk);
+  if (centre) {
+    double *part = nullptr, *colsum = nullptr, *mean = nullptr;
+    const int64_t warps = (int64_t)grid * 8;
+    BA_TRY(bufs.alloc(&part, (size_t)warps * n));
+    BA_TRY(bufs.alloc(&colsum, (size_t)n));
+    BA_TRY(bufs.alloc(&mean, (size_t)n));
+    col_partial_kernel<<<grid, 256, 0, s>>>(N, n, dW, part);
+    colsum_finish_kernel<<<(n + 63) / 64, 64, 0, s>>>(part, warps, n, colsum);
+    pad_rows_centred_kernel<<<grid, 256, 0, s>>>(N, n, ld, dW, colsum, mean, Wk);
+    g_launch_count += 2;
+    if (mean_out)
+      BA_CUDA(cudaMemcpyAsync(mean_out, mean, (size_t)n * d,
+                              mem == BA_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  } else {
+    pad_rows_kernel<<<grid, 256, 0, s>>>(N, n, ld, dW, Wk);
+  }
   GramWorkspace ws;
   int st = gram_prepare(&ws, ld, k_pad, num_sms, s);
   if (st == BA_OK) st = leading_subspace(n, ld, k_pad, &ws, Wk, P, G, V, U4, ev, status, false, s);
@@ -1099,6 +1142,17 @@ extern "C" int ba_factorize_rank4(int device, int64_t n_cols, int32_t n_rows, co
   }
   gram_release(&ws, s);
   return st;
+}
+
+extern "C" int ba_factorize_rank4(int device, int64_t n_cols, int32_t n_rows, const double* Wt, double* M_out,
+                                  double* S_out, double* sigma_out, int mem, void* stream) {
+  return factorize_rank4_impl(device, n_cols, n_rows, Wt, false, nullptr, M_out, S_out, sigma_out, mem, stream);
+}
+
+extern "C" int ba_factorize_centred_rank4(int device, int64_t n_cols, int32_t n_rows, const double* Wt,
+                                          double* mean_out, double* M_out, double* S_out, double* sigma_out,
+                                          int mem, void* stream) {
+  return factorize_rank4_impl(device, n_cols, n_rows, Wt, true, mean_out, M_out, S_out, sigma_out, mem, stream);
 }
 
 extern "C" int ba_projective_depth_primary(int device, int64_t n_points, int32_t n_images, const double* x,

@@ -315,9 +315,10 @@ def launch_count() -> int:
     return int(_cabi.load().ba_launch_count())
 
 
-def fp64_peak(device: int = 0, dmma: bool = True) -> float:
+def fp64_peak(device: int = 0, dmma=True) -> float:
+    """TFLOP/s of a register-resident loop: dmma=True DMMA.8x8x4, False DFMA, 2 both interleaved."""
     v = C.c_double()
-    _cabi.check(_cabi.load().ba_fp64_peak(device, 1 if dmma else 0, C.byref(v)))
+    _cabi.check(_cabi.load().ba_fp64_peak(device, 2 if dmma == 2 else (1 if dmma else 0), C.byref(v)))
     return v.value
 
 

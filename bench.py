@@ -555,7 +555,9 @@ def measure(ctx: Ctx, name: str, strong: bool, K: int, W: int, *, full_run_tol=N
         tot = sum(v["ms"] for k, v in prof.items() if k in ("k1", "k2", "k3", "k4", "cost", "other"))
         if sc.dense and prof["syrk"]["launches"] > 0:
             avg_ms = prof["syrk"]["ms"] / prof["syrk"]["launches"]
-            kernel = "syrk_dmma_kernel (K3, Schur SYRK on FP64 tensor cores)"
+            kernel = "syrk_tma_kernel (K3, Schur SYRK on FP64 tensor cores, DMMA.8x8x4 fed by TMA)" \
+                if ctx.engine_mod.syrk_feed() == "tma" else \
+                "syrk_dmma_kernel (K3, Schur SYRK on FP64 tensor cores)"
             share = prof["syrk"]["ms"] / tot if tot > 0 else None
         else:
             avg_ms = prof["k3"]["ms"] / max(st_prof.solves, 1)

@@ -243,7 +243,8 @@ int64_t ba_launch_count(void);
 int ba_profile_enable(ba_engine* e, int on);
 int ba_profile_get(ba_engine* e, const char* group, double* total_ms, int64_t* launches);
 int ba_profile_reset(ba_engine* e);
-/* FP64 peak micro-benchmarks (register-resident DMMA.8x8x4 / DFMA loops): TFLOP/s. */
+/* FP64 peak micro-benchmarks (register-resident loops): TFLOP/s.  use_dmma = 1: DMMA.8x8x4,
+ * 0: DFMA, 2: both interleaved with equal FMA counts (do they share the FP64 datapath?). */
 int ba_fp64_peak(int device, int use_dmma, double* tflops);
 /* How the 128-tile Schur SYRK / Cholesky trailing update gets its operands: 1 = TMA tensor copies +
  * mbarriers with a producer warp (cp.async.bulk.tensor, SASS UTMALDG), 0 = cp.async (LDGSTS; set
@@ -303,6 +304,16 @@ int ba_depth_dual_probe(double* V4, double* R60, double* W12, double* e, double*
  * leading eigenspace is computed.  Singular vectors are defined up to sign, as in LAPACK. */
 int ba_factorize_rank4(int device, int64_t n_cols, int32_t n_rows, const double* Wt, double* M_out,
                        double* S_out, double* sigma_out, int mem, void* stream);
+
+/* The factorisation step of the affine self-calibrations (reference lib/affine_camera_calibration.py:
+ * _get_observation_matrix :224-240 followed by np.linalg.svd at :21, :70, :154): every row of W
+ * (n_rows = 2 n_images, one image coordinate each) is first centred over the points -- here every
+ * column of the point-major array Wt [n_cols][n_rows], which is the reference's np.hstack(data_list)
+ * as it lies in memory -- mean_out[n_rows] (may be NULL) receives the means (the image centroids t),
+ * then the rank-4 factorisation above runs on the centred matrix; the callers use its three leading
+ * components.  Same size limits and sign convention as ba_factorize_rank4. */
+int ba_factorize_centred_rank4(int device, int64_t n_cols, int32_t n_rows, const double* Wt, double* mean_out,
+                               double* M_out, double* S_out, double* sigma_out, int mem, void* stream);
 
 #ifdef __cplusplus
 }
