@@ -23,6 +23,11 @@ def __getattr__(name):
         from . import projective_depth
 
         return getattr(projective_depth, name)
+    if name in ("orthographic_self_calibration", "symmetric_affine_self_calibration",
+                "paraperspective_self_calibration"):
+        from . import affine_calibration
+
+        return getattr(affine_calibration, name)
     if name == "Engine":
         from . import engine
 
