@@ -119,7 +119,7 @@ struct ba_engine {
   int64_t* cam_ptr = nullptr;  // [M+1] (sparse)
   int32_t* cm_perm = nullptr;  // [nobs] observation ids sorted by camera (sparse)
   uint32_t* bits = nullptr;    // [M][Wp] per camera: bitmap over points (sparse)
-  int64_t Wp = 0;              // words per camera bitmap, padded to a multiple of 128
+  int64_t Wp = 0;              // words per camera bitmap, padded to a multiple of 256
   bool have_obs = false, have_state = false;
 
   // state: [0] current, [1] trial

@@ -291,7 +291,7 @@ static int create_engine(const ba_problem* p, ba_engine** out) {
     A(dev_alloc(&e->obs_pt, (size_t)e->nobs));
     A(dev_alloc(&e->cm_perm, (size_t)e->nobs));
     A(dev_alloc(&e->cam_ptr, (size_t)e->M + 1));
-    e->Wp = round_up64((e->N + 31) / 32, 128);
+    e->Wp = round_up64((e->N + 31) / 32, 256);  // whole groups of 256 words: 32 lanes x 8 words (pair kernels)
     A(dev_alloc(&e->bits, (size_t)e->M * e->Wp));
     A(dev_alloc(&e->PT, (size_t)e->N * kPT));
   }

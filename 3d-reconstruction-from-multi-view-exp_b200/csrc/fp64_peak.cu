@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, 
   if (s == 123.456) out[0] = s;
 }
 
-__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
+__global__ void __launch_bounds__(1024) dfma_peak_kernel(double* out, int iters, double seed) {
   double a = seed + threadIdx.x * 1e-9, b = seed * 0.5;
   double c[16];
 #pragma unroll
@@ -77,7 +77,12 @@ int fp64_peak(int device, int use_dmma, double* tflops) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+  // modes 100 + w: the DFMA loop with w warps per SM (one block per SM): FP64 rate at low occupancy
+  const bool low_occ = use_dmma >= 100;
+  const int blocks = prop.multiProcessorCount * (low_occ ? 1 : 8), threads = low_occ ? 32 * (use_dmma - 100) : 256,
+            iters = 20000;
+  if (low_occ) use_dmma = 0;
+  if (threads < 32 || threads > 1024) { set_error("bad mode"); cudaFree(out); return BA_ERR_INVALID; }
   double best = 0.0;
   for (int rep = 0; rep < 4; ++rep) {
     cudaEventRecord(e0);

@@ -29,11 +29,15 @@
 //
 // schur_diag_kernel: the diagonal blocks P[9i..][9i..] and the rhs row, a segmented reduction over
 // the camera's observations in camera-major order (fixed chunking and order).
+#include <cstdlib>
+
 #include "ba_common.cuh"
 
 namespace ba {
 
-constexpr int kPS = 14;            // doubles per point row in shared memory (112 B = 7 x 16: odd -> conflict-free LDS.128)
+constexpr int kPS = 14;            // register variant: doubles per point row in shared memory (112 B = 7 x 16: odd -> conflict-free LDS.128)
+constexpr int kPSD = 10;           // DMMA variant: 80 B = 5 x 16 (odd as well); the 9 doubles in use are the first 5 pieces
+constexpr int kPieces = 5;         // 16-byte pieces gathered per point row
 constexpr int kPairTile = 32;      // pairs are scheduled in kPairTile x kPairTile tiles of (i, k)
 constexpr int kDiagPart = 54;      // 45 unique entries of the diagonal block + 9 rhs entries
 constexpr int kQueue = 128;        // queue capacity (point ids)
@@ -65,6 +69,15 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// 1 / d to <= ~1 ulp: hardware seed and two Newton steps (a full division is ~20 instructions)
+__device__ __forceinline__ double rcp_nr(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  r = fma(r, fma(-d, r, 1.0), r);
+  r = fma(r, fma(-d, r, 1.0), r);
+  return r;
+}
+
 // Pair number t -> (i, k), k < i.  Pairs are ordered tile by tile (kPairTile x kPairTile cameras),
 // so that the warps resident at any time share few bitmaps and walk the points in step.
 __device__ __forceinline__ bool pair_from_linear(int64_t t, int M, int& i, int& k) {
@@ -81,7 +94,7 @@ __device__ __forceinline__ bool pair_from_linear(int64_t t, int M, int& i, int& 
 }
 
 struct PairSmem {
-  double stage[2][32 * kPS];  // [stage][point of the round][kPS]: X (3), Vd^-1 (6: 00 01 02 11 12 22)
+  double stage[2][32 * kPSD];  // [stage][point of the round][kPS]: X (3), Vd^-1 (6: 00 01 02 11 12 22)
   double cam[2][20];          // table rows of camera i and k (K1's layout) + 1/f, u0/f0, v0/f0, 1/f0
   double ifrag[2 * kFragX];   // [x][lane][8]: first 8 entries of Jc_i row x of the lane's point (DMMA A operand)
   double tfrag[2 * kFragX];   // [x][lane][8]: first 8 entries of row x of G Jc_k            (DMMA B operand)
@@ -115,7 +128,8 @@ __device__ __forceinline__ SideJac side_jacobian(const double* __restrict__ c, d
   return s;
 }
 
-__global__ void __launch_bounds__(32, 12)
+template <int MINB>
+__global__ void __launch_bounds__(32, MINB)
 schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bits,
                    const double* __restrict__ camtab, double f0, const double* __restrict__ PT,
                    double* __restrict__ P, int ld, const ba_lm_state* ctl) {
@@ -168,7 +182,7 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
     double2* t1s = reinterpret_cast<double2*>(sm.tfrag + kFragX + lane * 8);
     const int sw = (lane >> 1) & 3;
     if (lane < cnt) {
-      const double* pt = sm.stage[st] + lane * kPS;
+      const double* pt = sm.stage[st] + lane * kPSD;
       const double2 x01 = *reinterpret_cast<const double2*>(pt);
       const double2 x2v = *reinterpret_cast<const double2*>(pt + 2);  // X2, V00
       const double2 v12 = *reinterpret_cast<const double2*>(pt + 4);  // V01, V02
@@ -259,54 +273,33 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
     }
   };
 
-  // Issue the gather of the next round (queue[0, cnt)), move the rest of the queue down, then
-  // compute the previous round.
-  auto round = [&](int cnt) {
-    const uint32_t sa = s_addr + (uint32_t)(rounds & 1) * (32 * kPS * 8);
-#pragma unroll
-    for (int u = 0; u < 6; ++u) {
-      const int p = lane + 32 * u;
-      const int row = (p * 171) >> 10;  // p / 6 for p < 192
-      const int piece = p - 6 * row;
-      int j;
-      asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(j) : "r"(q_addr + 4u * row));
-      if (row < cnt) cp_async16(sa + (row * kPS + 2 * piece) * 8, PT + (size_t)j * kPT + 2 * piece);
-    }
-    cp_commit();
-    qn -= cnt;
-    {
-      // queue[32 + x] -> queue[x]
-      int up[3];
-#pragma unroll
-      for (int u = 0; u < 3; ++u) up[u] = sm.queue[32 * (u + 1) + lane];
-      __syncwarp();
-#pragma unroll
-      for (int u = 0; u < 3; ++u) sm.queue[32 * u + lane] = up[u];
-    }
-    if (rounds > 0) {
-      cp_wait<1>();
-      __syncwarp();
-      compute((rounds & 1) ^ 1, cnt_prev);
-    }
-    __syncwarp();
-    cnt_prev = cnt;
-    ++rounds;
-  };
-
-  // bitmap words are fetched one batch ahead
-  uint4 wi = bi[0], wk = bk[0];
-  for (int64_t w0 = 0; w0 < Wp; w0 += 128) {
-    const uint4 ci = wi, ck = wk;
-    if (w0 + 128 < Wp) {
-      wi = bi[(w0 + 128) >> 2];
-      wk = bk[(w0 + 128) >> 2];
-    }
-    uint64_t c0 = ((uint64_t)(ci.y & ck.y) << 32) | (ci.x & ck.x);
-    uint64_t c1 = ((uint64_t)(ci.w & ck.w) << 32) | (ci.z & ck.z);
-    const int jbase = (int)(w0 + 4 * lane) * 32;
-    while (__any_sync(0xffffffffu, (c0 | c1) != 0ull)) {
+  // One loop, one instance of compute(): refill the queue from the bitmaps until it holds a full
+  // round (or the scan is over), issue that round's gather, compute the round gathered before.
+  uint4 wi = bi[0], wk = bk[0];  // bitmap words are fetched one batch ahead
+  int64_t w0 = 0;                // first word of the next batch
+  uint64_t h0 = 0ull, h1 = 0ull; // hits of the current batch not queued yet
+  int jbase = 0;
+  bool scanning = true;
+  for (;;) {
+    while (scanning && qn < 32) {
+      if (!__any_sync(0xffffffffu, (h0 | h1) != 0ull)) {
+        if (w0 >= Wp) {
+          scanning = false;
+          break;
+        }
+        const uint4 ci = wi, ck = wk;
+        if (w0 + 128 < Wp) {
+          wi = bi[(w0 + 128) >> 2];
+          wk = bk[(w0 + 128) >> 2];
+        }
+        h0 = ((uint64_t)(ci.y & ck.y) << 32) | (ci.x & ck.x);
+        h1 = ((uint64_t)(ci.w & ck.w) << 32) | (ci.z & ck.z);
+        jbase = (int)(w0 + 4 * lane) * 32;
+        w0 += 128;
+        continue;
+      }
       // exclusive prefix of the hit counts -> queue slots; hits that do not fit wait for the next pass
-      const int n = __popcll(c0) + __popcll(c1);
+      const int n = __popcll(h0) + __popcll(h1);
       int incl = n;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
@@ -315,27 +308,53 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
       }
       const int total = __shfl_sync(0xffffffffu, incl, 31);
       int pos = qn + incl - n;
-      while (c0 != 0ull && pos < kQueue) {
-        const int b = __ffsll((long long)c0) - 1;
-        c0 &= c0 - 1;
+      while (h0 != 0ull && pos < kQueue) {
+        const int b = __ffsll((long long)h0) - 1;
+        h0 &= h0 - 1;
         sm.queue[pos++] = jbase + b;
       }
-      while (c0 == 0ull && c1 != 0ull && pos < kQueue) {
-        const int b = __ffsll((long long)c1) - 1;
-        c1 &= c1 - 1;
+      while (h0 == 0ull && h1 != 0ull && pos < kQueue) {
+        const int b = __ffsll((long long)h1) - 1;
+        h1 &= h1 - 1;
         sm.queue[pos++] = jbase + 64 + b;
       }
       qn = qn + total < kQueue ? qn + total : kQueue;
       __syncwarp();
-      while (qn >= 32) round(32);
     }
-  }
-  if (qn > 0) round(qn);
-  if (rounds > 0) {
-    cp_wait<0>();
+    const int cnt = qn < 32 ? qn : 32;
+    if (cnt == 0 && cnt_prev == 0) break;
+    if (cnt > 0) {
+      // gather of this round (queue[0, cnt)) into the stage the previous round does not occupy
+      const uint32_t sa = s_addr + (uint32_t)(rounds & 1) * (32 * kPSD * 8);
+#pragma unroll
+      for (int u = 0; u < kPieces; ++u) {
+        const int p = lane + 32 * u;
+        const int row = (p * 205) >> 10;  // p / 5 for p < 160
+        const int piece = p - kPieces * row;
+        int j;
+        asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(j) : "r"(q_addr + 4u * row));
+        if (row < cnt) cp_async16(sa + (row * kPSD + 2 * piece) * 8, PT + (size_t)j * kPT + 2 * piece);
+      }
+      qn -= cnt;
+      int up[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) up[u] = sm.queue[32 * (u + 1) + lane];
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 3; ++u) sm.queue[32 * u + lane] = up[u];
+    }
+    cp_commit();  // possibly empty: keeps "all but the newest group" = the previous round's gather
+    if (cnt_prev > 0) {
+      cp_wait<1>();
+      __syncwarp();
+      compute((rounds & 1) ^ 1, cnt_prev);
+    }
     __syncwarp();
-    compute((rounds - 1) & 1, cnt_prev);
+    cnt_prev = cnt;
+    ++rounds;
   }
+  cp_wait<0>();
+  __syncwarp();
 
   // leading 8x8 straight from the C fragments; row 8, column 8 and the corner after a fixed-order
   // butterfly over the 32 lanes.  Rows / columns of gauge-pinned parameters (:62-72) are zero.
@@ -365,6 +384,250 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     if (((mask_i >> 8) | (mask_k >> 8)) & 1u) v = 0.0;
     if (lane == 16) P[(size_t)(9 * i + 8) * ld + 9 * k + 8] = v;
+  }
+}
+
+// ---- register-accumulator variant -----------------------------------------------------------------
+// What ncu said about the kernel above (profiles/r2_pairs_*): DMMA shares the FP64 datapath with DFMA
+// (fp64_peak mode 2: 32 TF/s in sum), so the tensor instructions buy no arithmetic, and building
+// their fragments costs 128 shared-memory wavefronts per 32 pair-points; and, by stall samples, 60 %
+// of the time went into finding the common points -- the warp-wide prefix scan, the divergent
+// bit-extraction loops, the queue and the index arithmetic of the gather (~400 integer instructions
+// per round) -- not into the products.  This variant changes both:
+//   * every lane keeps the whole 9 x 9 block of the pair in 81 FP64 registers and adds its point's
+//     Jc_i^T (G Jc_k) with 144 DFMAs (the structural zeros of Jc_i skipped): no fragments, no
+//     shuffles, 255 registers, eight warps per SM, independent accumulator chains;
+//   * every lane scans the bitmaps ON ITS OWN: the point range is cut into groups of 256 points that
+//     the lanes claim one at a time, a lane holds the AND of its current group in four
+//     64-bit registers, takes its next common point with one find-first-set, and computes the point
+//     it took one round earlier (the 32 rows of a round are gathered by the warp together, five
+//     consecutive lanes per row, with 16-byte cp.async).  No queue, no prefix sums, no warp-level compaction; the next
+//     group's bitmap words are prefetched into a private shared-memory slot by cp.async as well.
+//     A lane whose new group is empty idles for that round (3 % at 10 % visibility).
+// The 81 per-lane sums meet once per pair, through shared memory (the staging rows, free by then),
+// in lane order.  Order of summation depends on the data only: bit-reproducible.
+constexpr int kGroupWords = 8;  // 256 points per lane and group
+
+struct PairRegSmem {
+  double stage[2][32 * kPS];  // [parity][lane][kPS] private rows; reduction scratch [27][33] at the end
+  uint4 slot[2][4][32];       // [parity][camera i lo, i hi, camera k lo, k hi][lane]: prefetched bitmap group
+  double cam[2][20];
+};
+static_assert(27 * 33 <= 2 * 32 * kPS, "reduction scratch must fit the staging buffers");
+
+__global__ void __launch_bounds__(32, 8)
+schur_pairs_reg_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bits,
+                       const double* __restrict__ camtab, double f0, const double* __restrict__ PT,
+                       double* __restrict__ P, int ld, const ba_lm_state* ctl) {
+  if (ctl && ctl->done) return;
+  int i, k;
+  if (!pair_from_linear(blockIdx.x, M, i, k)) return;
+  __shared__ __align__(16) PairRegSmem sm;
+  const int lane = threadIdx.x;
+  {
+    const int which = lane >> 4, c = lane & 15;
+    const double v = camtab[(size_t)(which ? k : i) * kCamTab + c];
+    sm.cam[which][c] = v;
+    __syncwarp();
+    if (c == 0) {
+      const double f = sm.cam[which][12], u0 = sm.cam[which][13], v0 = sm.cam[which][14];
+      sm.cam[which][16] = 1.0 / f;
+      sm.cam[which][17] = u0 / f0;
+      sm.cam[which][18] = v0 / f0;
+      sm.cam[which][19] = 1.0 / f0;
+    }
+    __syncwarp();
+  }
+
+  double acc[9][9];
+#pragma unroll
+  for (int a = 0; a < 9; ++a)
+#pragma unroll
+    for (int b = 0; b < 9; ++b) acc[a][b] = 0.0;
+
+  auto compute = [&](int st) {
+    const double* pt = sm.stage[st] + lane * kPS;
+    const double2 x01 = *reinterpret_cast<const double2*>(pt);
+    const double2 x2v = *reinterpret_cast<const double2*>(pt + 2);  // X2, V00
+    const double2 v12 = *reinterpret_cast<const double2*>(pt + 4);  // V01, V02
+    const double2 v34 = *reinterpret_cast<const double2*>(pt + 6);  // V11, V12
+    const double v22 = pt[8];
+    const double v00 = x2v.y, v01 = v12.x, v02 = v12.y, v11 = v34.x, v12_ = v34.y;
+    const SideJac si = side_jacobian(sm.cam[0], x01.x, x01.y, x2v.x);
+    double t0[9], t1[9];
+    {
+      const SideJac sk = side_jacobian(sm.cam[1], x01.x, x01.y, x2v.x);
+      // G = 4 Jx_i Vd^-1 Jx_k^T with the four 1 / r^2 factors folded into one scale
+      const double rr = si.r * sk.r;
+      const double rr2 = rr * rr;
+      const double sc = 4.0 * rcp_nr(rr2 * rr2);
+      double g00, g01, g10, g11;
+      {
+        const double m0 = v00 * sk.aX[0] + v01 * sk.aX[1] + v02 * sk.aX[2];
+        const double m1 = v01 * sk.aX[0] + v11 * sk.aX[1] + v12_ * sk.aX[2];
+        const double m2 = v02 * sk.aX[0] + v12_ * sk.aX[1] + v22 * sk.aX[2];
+        g00 = sc * (si.aX[0] * m0 + si.aX[1] * m1 + si.aX[2] * m2);
+        g10 = sc * (si.bX[0] * m0 + si.bX[1] * m1 + si.bX[2] * m2);
+      }
+      {
+        const double m0 = v00 * sk.bX[0] + v01 * sk.bX[1] + v02 * sk.bX[2];
+        const double m1 = v01 * sk.bX[0] + v11 * sk.bX[1] + v12_ * sk.bX[2];
+        const double m2 = v02 * sk.bX[0] + v12_ * sk.bX[1] + v22 * sk.bX[2];
+        g01 = sc * (si.aX[0] * m0 + si.aX[1] * m1 + si.aX[2] * m2);
+        g11 = sc * (si.bX[0] * m0 + si.bX[1] * m1 + si.bX[2] * m2);
+      }
+      // rows of G Jc_k; Jc_k row a = [af, au, 0, -aX, aX x d], row b = [bf, 0, au, -bX, bX x d]
+      t0[0] = g00 * sk.af + g01 * sk.bf;  t1[0] = g10 * sk.af + g11 * sk.bf;
+      t0[1] = g00 * sk.au;                t1[1] = g10 * sk.au;
+      t0[2] = g01 * sk.au;                t1[2] = g11 * sk.au;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        t0[3 + m] = -(g00 * sk.aX[m] + g01 * sk.bX[m]);
+        t1[3 + m] = -(g10 * sk.aX[m] + g11 * sk.bX[m]);
+      }
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const int m1 = (m + 1) % 3, m2 = (m + 2) % 3;
+        const double aw = sk.aX[m1] * sk.d[m2] - sk.aX[m2] * sk.d[m1];
+        const double bw = sk.bX[m1] * sk.d[m2] - sk.bX[m2] * sk.d[m1];
+        t0[6 + m] = g00 * aw + g01 * bw;
+        t1[6 + m] = g10 * aw + g11 * bw;
+      }
+    }
+    // block += Jc_i^T [t0; t1], row by row of Jc_i^T; its structural zeros are skipped
+#pragma unroll
+    for (int b = 0; b < 9; ++b) {
+      acc[0][b] = fma(si.af, t0[b], fma(si.bf, t1[b], acc[0][b]));
+      acc[1][b] = fma(si.au, t0[b], acc[1][b]);
+      acc[2][b] = fma(si.au, t1[b], acc[2][b]);
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+#pragma unroll
+      for (int b = 0; b < 9; ++b) acc[3 + m][b] = fma(-si.aX[m], t0[b], fma(-si.bX[m], t1[b], acc[3 + m][b]));
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      const int m1 = (m + 1) % 3, m2 = (m + 2) % 3;
+      const double aw = si.aX[m1] * si.d[m2] - si.aX[m2] * si.d[m1];
+      const double bw = si.bX[m1] * si.d[m2] - si.bX[m2] * si.d[m1];
+#pragma unroll
+      for (int b = 0; b < 9; ++b) acc[6 + m][b] = fma(aw, t0[b], fma(bw, t1[b], acc[6 + m][b]));
+    }
+  };
+
+  // ---- the lanes' walk over the groups -----------------------------------------------------------
+  // Groups are CLAIMED, not owned: a lane that has moved its waiting group into its registers takes
+  // the next unclaimed group (ballot + popc, warp-uniform counter) and starts its prefetch.  Every
+  // lane thus always has one group in flight behind the one it is working on, and the lanes finish
+  // within one group of each other (with fixed ownership the warp waits for its unluckiest lane:
+  // +2 sigma of a Poisson count, 28 % of all rounds at 10^5 points).  The claim order depends on
+  // the bitmaps only: still bit-reproducible.
+  const int n_groups = (int)(Wp / kGroupWords);
+  const uint32_t slot_addr = (uint32_t)__cvta_generic_to_shared(&sm.slot[0][0][lane]);
+  const uint32_t stage_addr0 = (uint32_t)__cvta_generic_to_shared(sm.stage[0]);
+  const uint32_t* gi = bits + (size_t)i * Wp;
+  const uint32_t* gk = bits + (size_t)k * Wp;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint64_t m0 = 0ull, m1 = 0ull, m2 = 0ull, m3 = 0ull;  // common points of the current group, not taken yet
+  int base = 0;          // point id of the current group's bit 0
+  int next = 0;          // first unclaimed group (warp-uniform)
+  int slot_g = -1;       // group waiting (or arriving) in this lane's slot, -1: none
+  int par = 0;           // which of the lane's two slots the next claim uses
+  bool prev = false;     // the lane took a point in the previous round
+  for (int r = 0;; ++r) {
+    cp_wait<0>();  // the previous round's point rows (copied by five lanes each) and bitmap groups
+    __syncwarp();
+    if ((m0 | m1 | m2 | m3) == 0ull && slot_g >= 0) {
+      const uint4* sl = &sm.slot[par ^ 1][0][lane];
+      const uint4 a0 = sl[0], a1 = sl[32], b0 = sl[64], b1 = sl[96];
+      m0 = ((uint64_t)(a0.y & b0.y) << 32) | (a0.x & b0.x);
+      m1 = ((uint64_t)(a0.w & b0.w) << 32) | (a0.z & b0.z);
+      m2 = ((uint64_t)(a1.y & b1.y) << 32) | (a1.x & b1.x);
+      m3 = ((uint64_t)(a1.w & b1.w) << 32) | (a1.z & b1.z);
+      base = slot_g * (32 * kGroupWords);
+      slot_g = -1;
+    }
+    {
+      const uint32_t need = __ballot_sync(0xffffffffu, slot_g < 0);
+      const int g = next + __popc(need & lt_mask);
+      if (slot_g < 0 && g < n_groups) {
+        const uint32_t dst = slot_addr + (uint32_t)par * (uint32_t)sizeof(sm.slot[0]);
+        const size_t off = (size_t)g * kGroupWords;
+        cp_async16(dst, gi + off);
+        cp_async16(dst + 512u, gi + off + 4);
+        cp_async16(dst + 1024u, gk + off);
+        cp_async16(dst + 1536u, gk + off + 4);
+        slot_g = g;
+        par ^= 1;
+      }
+      next += __popc(need);
+      if (next > n_groups) next = n_groups;
+    }
+    const bool hit = (m0 | m1 | m2 | m3) != 0ull;
+    int jhit = -1;
+    if (hit) {
+      int b;
+      if (m0 != 0ull) {
+        b = __ffsll((long long)m0) - 1;
+        m0 &= m0 - 1;
+      } else if (m1 != 0ull) {
+        b = 64 + __ffsll((long long)m1) - 1;
+        m1 &= m1 - 1;
+      } else if (m2 != 0ull) {
+        b = 128 + __ffsll((long long)m2) - 1;
+        m2 &= m2 - 1;
+      } else {
+        b = 192 + __ffsll((long long)m3) - 1;
+        m3 &= m3 - 1;
+      }
+      jhit = base + b;
+    }
+    // The 32 point rows are gathered by the warp together, five consecutive lanes per row: one
+    // instruction then touches ~7 rows instead of 32 (the L1 takes ~2 cycles per 128-byte line an
+    // instruction touches: lane-private gathers cost more than the arithmetic of the round).
+    {
+      const uint32_t dst = stage_addr0 + (uint32_t)(r & 1) * (32 * kPS * 8);
+#pragma unroll
+      for (int u = 0; u < kPieces; ++u) {
+        const int p = lane + 32 * u;
+        const int row = (p * 205) >> 10;  // p / 5 for p < 160
+        const int piece = p - kPieces * row;
+        const int jr = __shfl_sync(0xffffffffu, jhit, row);
+        if (jr >= 0) cp_async16(dst + (uint32_t)(row * kPS + 2 * piece) * 8u, PT + (size_t)jr * kPT + 2 * piece);
+      }
+    }
+    cp_commit();
+    if (prev) compute((r & 1) ^ 1);
+    prev = hit;
+    if (!__any_sync(0xffffffffu, hit || slot_g >= 0)) break;  // `hit` lanes still owe one compute
+  }
+  __syncwarp();
+
+  // 81 sums over the 32 lanes, 27 at a time through the (now free) staging buffers: lane e adds
+  // entry e of every lane in lane order.  Rows / columns of gauge-pinned parameters (:62-72) are zero.
+  const uint32_t mask_i = gauge_mask(i, axis), mask_k = gauge_mask(k, axis);
+  double* scratch = sm.stage[0];
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+    for (int e = 0; e < 27; ++e) scratch[e * 33 + lane] = acc[3 * pass + e / 9][e % 9];
+    __syncwarp();
+    if (lane < 27) {
+      const double* row = scratch + lane * 33;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+      for (int q = 0; q < 32; q += 4) {
+        s0 += row[q];
+        s1 += row[q + 1];
+        s2 += row[q + 2];
+        s3 += row[q + 3];
+      }
+      const int a = 3 * pass + lane / 9, b = lane % 9;
+      const bool pin = ((mask_i >> a) | (mask_k >> b)) & 1u;
+      P[(size_t)(9 * i + a) * ld + 9 * k + b] = pin ? 0.0 : (s0 + s1) + (s2 + s3);
+    }
+    __syncwarp();
   }
 }
 
@@ -453,10 +716,23 @@ int launch_schur_sparse(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
     set_error("too many camera pairs for one launch (M=%d)", e->M);
     return BA_ERR_INVALID;
   }
-  BA_CUDA(cudaFuncSetAttribute(schur_pairs_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                               (int)cudaSharedmemCarveoutMaxShared));
-  schur_pairs_kernel<<<(unsigned)n_items, 32, 0, s>>>(e->M, e->axis, e->Wp, e->bits, e->camtab[0], e->f0,
-                                                     e->PT, e->P(), e->n_pad, ctl);
+  // BA_PAIRS_REG: the register-accumulator variant below (A/B timing: 40.0 against 38.5 ms at 1000 x 200k)
+  static const bool use_reg = std::getenv("BA_PAIRS_REG") != nullptr;
+  if (!use_reg) {
+    // 12 warps per SM at 168 registers; BA_PAIRS_OCC15: 15 warps at 128 registers (A/B timing: 39.3 against
+    // 38.5 ms at 1000 x 200k -- the kernel is not occupancy-bound)
+    static const bool occ15 = std::getenv("BA_PAIRS_OCC15") != nullptr;
+    auto kern = occ15 ? schur_pairs_kernel<15> : schur_pairs_kernel<12>;
+    BA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 (int)cudaSharedmemCarveoutMaxShared));
+    kern<<<(unsigned)n_items, 32, 0, s>>>(e->M, e->axis, e->Wp, e->bits, e->camtab[0], e->f0, e->PT, e->P(),
+                                         e->n_pad, ctl);
+  } else {
+    BA_CUDA(cudaFuncSetAttribute(schur_pairs_reg_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 (int)cudaSharedmemCarveoutMaxShared));
+    schur_pairs_reg_kernel<<<(unsigned)n_items, 32, 0, s>>>(e->M, e->axis, e->Wp, e->bits, e->camtab[0], e->f0,
+                                                           e->PT, e->P(), e->n_pad, ctl);
+  }
   BA_LAUNCH_CHECK();
   return BA_OK;
 }

@@ -318,7 +318,8 @@ def launch_count() -> int:
 def fp64_peak(device: int = 0, dmma=True) -> float:
     """TFLOP/s of a register-resident loop: dmma=True DMMA.8x8x4, False DFMA, 2 both interleaved."""
     v = C.c_double()
-    _cabi.check(_cabi.load().ba_fp64_peak(device, 2 if dmma == 2 else (1 if dmma else 0), C.byref(v)))
+    mode = int(dmma) if isinstance(dmma, int) and not isinstance(dmma, bool) and dmma >= 2 else (1 if dmma else 0)
+    _cabi.check(_cabi.load().ba_fp64_peak(device, mode, C.byref(v)))
     return v.value
 
 
