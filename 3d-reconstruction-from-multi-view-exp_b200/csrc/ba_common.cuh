@@ -253,6 +253,79 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
 }
 #endif
 
+#ifdef __CUDACC__
+// Shared-memory copy of a camera table: rows padded to 17 doubles (conflict-free when the lanes of a
+// warp read one column of 32 consecutive rows, the dense-visibility pattern).
+constexpr int kTabStride = kCamTab + 1;
+__host__ __device__ constexpr size_t tab_smem_doubles(int M) { return ((size_t)M * kTabStride + 1) & ~(size_t)1; }
+
+// Jacobian rows of ONE observation from the camera's table row T (rows of K R^T (9), t (3), f, u0,
+// v0) and the point X -- reference :283-427 (_calc_pqr, _calc_X_diff_pqr, _calc_{f,u,t,R}_diff_pqr).
+// K1 stores these rows (JP, JC); the dense K2b and the dense point update re-derive them instead of
+// reading 224 B per observation back.  Every operation is pinned (explicit fma / __dmul_rn, no
+// compiler contraction), so all callers get the same bits.
+struct ObsJacobian {
+  double p, q, r;       // projection before the division
+  double ax[3], bx[3];  // d e0 / dX, d e1 / dX                         = JP[2..4], JP[5..7]
+  double ja[9], jb[9];  // d e0 / d(f, u0, v0, t, w), d e1 / d(...)     = JC[2..10], JC[11..19]
+};
+__device__ __forceinline__ void obs_jacobian(const double* T, double x0, double x1, double x2, double f0,
+                                             ObsJacobian& J) {
+  const double gp0 = T[0], gp1 = T[1], gp2 = T[2];
+  const double gq0 = T[3], gq1 = T[4], gq2 = T[5];
+  const double gr0 = T[6], gr1 = T[7], gr2 = T[8];
+  const double fi = T[12], u0 = T[13], v0 = T[14];
+  const double d0 = x0 - T[9], d1 = x1 - T[10], d2 = x2 - T[11];
+  const double p = fma(gp2, d2, fma(gp1, d1, __dmul_rn(gp0, d0)));
+  const double q = fma(gq2, d2, fma(gq1, d1, __dmul_rn(gq0, d0)));
+  const double r = fma(gr2, d2, fma(gr1, d1, __dmul_rn(gr0, d0)));
+  J.p = p; J.q = q; J.r = r;
+  // a_theta = r dp/dtheta - p dr/dtheta, b_theta = r dq/dtheta - q dr/dtheta; J = (a, b) / r^2
+  const double ir2 = 1.0 / __dmul_rn(r, r);
+  const double a0 = fma(r, gp0, -__dmul_rn(p, gr0)), a1 = fma(r, gp1, -__dmul_rn(p, gr1)),
+               a2 = fma(r, gp2, -__dmul_rn(p, gr2));  // :450
+  const double b0 = fma(r, gq0, -__dmul_rn(q, gr0)), b1 = fma(r, gq1, -__dmul_rn(q, gr1)),
+               b2 = fma(r, gq2, -__dmul_rn(q, gr2));  // :459
+  const double af = __dmul_rn(r, fma(-(u0 / f0), r, p) / fi);  // :336
+  const double bf = __dmul_rn(r, fma(-(v0 / f0), r, q) / fi);  // :337
+  const double au = __dmul_rn(r, r / f0);                      // :350-356
+  // rotation: d(p, q, r) / dw = grad x (X - t) (:391-396)  =>  a_w = a_X x d, b_w = b_X x d
+  const double aw0 = fma(a1, d2, -__dmul_rn(a2, d1)), aw1 = fma(a2, d0, -__dmul_rn(a0, d2)),
+               aw2 = fma(a0, d1, -__dmul_rn(a1, d0));
+  const double bw0 = fma(b1, d2, -__dmul_rn(b2, d1)), bw1 = fma(b2, d0, -__dmul_rn(b0, d2)),
+               bw2 = fma(b0, d1, -__dmul_rn(b1, d0));
+  J.ax[0] = __dmul_rn(a0, ir2); J.ax[1] = __dmul_rn(a1, ir2); J.ax[2] = __dmul_rn(a2, ir2);
+  J.bx[0] = __dmul_rn(b0, ir2); J.bx[1] = __dmul_rn(b1, ir2); J.bx[2] = __dmul_rn(b2, ir2);
+  // camera row a: f, u0, v0, t (3) = -a_X (:368-376), w (3); row b likewise
+  J.ja[0] = __dmul_rn(af, ir2); J.ja[1] = __dmul_rn(au, ir2); J.ja[2] = 0.0;
+  J.ja[3] = -J.ax[0]; J.ja[4] = -J.ax[1]; J.ja[5] = -J.ax[2];
+  J.ja[6] = __dmul_rn(aw0, ir2); J.ja[7] = __dmul_rn(aw1, ir2); J.ja[8] = __dmul_rn(aw2, ir2);
+  J.jb[0] = __dmul_rn(bf, ir2); J.jb[1] = 0.0; J.jb[2] = J.ja[1];
+  J.jb[3] = -J.bx[0]; J.jb[4] = -J.bx[1]; J.jb[5] = -J.bx[2];
+  J.jb[6] = __dmul_rn(bw0, ir2); J.jb[7] = __dmul_rn(bw1, ir2); J.jb[8] = __dmul_rn(bw2, ir2);
+}
+// T = 2 Jx L^-T (2 x 3) from the point-side rows and m = L^-1 (lower), and one entry of
+// Y = Jc^T T (reference :128-132 through the Cholesky factor): pinned like obs_jacobian, K2b writes
+// Y with these and the dense point update re-derives the same bits.
+__device__ __forceinline__ void scaled_point_rows(const double* ax, const double* bx, double m00, double m10,
+                                                  double m11, double m20, double m21, double m22, double* ta,
+                                                  double* tb) {
+  ta[0] = 2.0 * __dmul_rn(ax[0], m00);
+  ta[1] = 2.0 * fma(ax[1], m11, __dmul_rn(ax[0], m10));
+  ta[2] = 2.0 * fma(ax[2], m22, fma(ax[1], m21, __dmul_rn(ax[0], m20)));
+  tb[0] = 2.0 * __dmul_rn(bx[0], m00);
+  tb[1] = 2.0 * fma(bx[1], m11, __dmul_rn(bx[0], m10));
+  tb[2] = 2.0 * fma(bx[2], m22, fma(bx[1], m21, __dmul_rn(bx[0], m20)));
+}
+__device__ __forceinline__ double y_entry(double ja, double jb, double ta, double tb) {
+  return fma(ja, ta, __dmul_rn(jb, tb));
+}
+// acc += x0 y0 + x1 y1, pinned: the block sums of K2a / the camera blocks, stored rows or re-derived
+__device__ __forceinline__ double pair_accumulate(double acc, double x0, double y0, double x1, double y1) {
+  return __dadd_rn(acc, fma(x1, y1, __dmul_rn(x0, y0)));
+}
+#endif
+
 // Grid of a kernel whose blocks loop over `items` work units with a stride of the grid: at most
 // `cap` blocks, and every block gets the same number of units (to within one) -- with the plain
 // min(items, cap) a count just above the cap gives a few blocks two units and everybody else one,
@@ -266,10 +339,11 @@ inline int balanced_blocks(int64_t items, int64_t cap) {
 // kernel launchers implemented in the .cu files (each returns a ba_status)
 int launch_cam_prep(ba_engine* e, int which, cudaStream_t s);
 int launch_cost(ba_engine* e, int which, int slot, cudaStream_t s);
-int launch_k1(ba_engine* e, cudaStream_t s, bool conditional);
+int launch_k1(ba_engine* e, cudaStream_t s, bool conditional, bool force_rows = false);
 int launch_k2a(ba_engine* e, cudaStream_t s, bool conditional);
 int launch_camera_blocks(ba_engine* e, cudaStream_t s, bool conditional);
 int launch_k2b(ba_engine* e, bool conditional, double c_host, cudaStream_t s);
+bool dense_matrix_free(const ba_engine* e);  // dense K2b / point update re-derive the Jacobian rows
 int launch_k3(ba_engine* e, bool conditional, cudaStream_t s);
 int syrk_plan_engine(ba_engine* e);
 int syrk_feed_is_tma();  // 1: the 128-tile SYRK is fed by TMA + mbarriers, 0: by cp.async (BA_SYRK_NO_TMA)

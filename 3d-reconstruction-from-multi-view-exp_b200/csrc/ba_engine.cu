@@ -785,6 +785,9 @@ int ba_buffer_read(ba_engine* e, int id, double* host_out, int64_t n_doubles, vo
   if (n_doubles != n) { set_error("buffer %d holds %lld doubles, caller asked for %lld", id, (long long)n, (long long)n_doubles); return BA_ERR_INVALID; }
   cudaStream_t s = (cudaStream_t)stream;
   BA_CUDA(cudaSetDevice(e->device));
+  // dense matrix-free engines do not keep the Jacobian rows: K1 writes them for this read
+  if ((id == BA_BUF_JP || id == BA_BUF_JC) && dense_matrix_free(e) && e->have_obs && e->have_state)
+    BA_TRY(launch_k1(e, s, false, true));
   BA_CUDA(cudaMemcpyAsync(host_out, p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
   BA_CUDA(cudaStreamSynchronize(s));
   return BA_OK;

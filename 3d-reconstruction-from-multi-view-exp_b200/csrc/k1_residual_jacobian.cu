@@ -49,12 +49,8 @@ int launch_cam_prep(ba_engine* e, int which, cudaStream_t s) {
   return BA_OK;
 }
 
-// Shared-memory copy of the camera table: rows padded to 17 doubles.  With dense visibility the
-// lanes of a warp read the same column of 32 consecutive rows; at the table's own stride (16
-// doubles = 128 B) they would all hit one bank pair (ncu: 8.7 bank conflicts per observation).
-constexpr int kTabStride = kCamTab + 1;
-__host__ __device__ constexpr size_t tab_smem_doubles(int M) { return ((size_t)M * kTabStride + 1) & ~(size_t)1; }
-
+// (kTabStride / tab_smem_doubles: the padded shared-memory camera table, see ba_common.cuh; at the
+// table's own stride of 16 doubles ncu counted 8.7 bank conflicts per observation.)
 constexpr int kK1Stage = 32 * 8 + 32 * 21;  // staging doubles per warp: point rows, camera rows
 
 // ---- K1 -------------------------------------------------------------------------------------
@@ -103,47 +99,25 @@ k1_residual_jacobian_kernel(int64_t nobs, int M, const int32_t* __restrict__ obs
       i = obs_cam[o];
       j = obs_pt[o];
     }
-    const double* T = tab + (size_t)i * TS;
-    const double gp0 = T[0], gp1 = T[1], gp2 = T[2];
-    const double gq0 = T[3], gq1 = T[4], gq2 = T[5];
-    const double gr0 = T[6], gr1 = T[7], gr2 = T[8];
-    const double fi = T[12], u0 = T[13], v0 = T[14];
-    const double d0 = X[3 * (size_t)j + 0] - T[9];
-    const double d1 = X[3 * (size_t)j + 1] - T[10];
-    const double d2 = X[3 * (size_t)j + 2] - T[11];
+    ObsJacobian J;
+    obs_jacobian(tab + (size_t)i * TS, X[3 * (size_t)j + 0], X[3 * (size_t)j + 1], X[3 * (size_t)j + 2], f0, J);
     const double2 m = xy[o];
-
-    const double p = gp0 * d0 + gp1 * d1 + gp2 * d2;
-    const double q = gq0 * d0 + gq1 * d1 + gq2 * d2;
-    const double r = gr0 * d0 + gr1 * d1 + gr2 * d2;
-    const double e0 = p / r - m.x / f0;  // :445
-    const double e1 = q / r - m.y / f0;  // :454
+    const double e0 = J.p / J.r - m.x / f0;  // :445
+    const double e1 = J.q / J.r - m.y / f0;  // :454
     acc += e0 * e0 + e1 * e1;
-
-    // a_theta = r dp/dtheta - p dr/dtheta, b_theta = r dq/dtheta - q dr/dtheta; J = (a,b)/r^2
-    const double ir2 = 1.0 / (r * r);
-    const double a0 = r * gp0 - p * gr0, a1 = r * gp1 - p * gr1, a2 = r * gp2 - p * gr2;  // :450
-    const double b0 = r * gq0 - q * gr0, b1 = r * gq1 - q * gr1, b2 = r * gq2 - q * gr2;  // :459
-    const double af = r * ((p - u0 / f0 * r) / fi);  // :336
-    const double bf = r * ((q - v0 / f0 * r) / fi);  // :337
-    const double au = r * (r / f0);                  // :350-356
-    // rotation: d(p,q,r)/dw = grad x (X - t) (:391-396) => a_w = a_X x d, b_w = b_X x d
-    const double aw0 = a1 * d2 - a2 * d1, aw1 = a2 * d0 - a0 * d2, aw2 = a0 * d1 - a1 * d0;
-    const double bw0 = b1 * d2 - b2 * d1, bw1 = b2 * d0 - b0 * d2, bw2 = b0 * d1 - b1 * d0;
 
     double* wp = st + lane * 8;
     wp[0 ^ swz] = e0; wp[1 ^ swz] = e1;
-    wp[2 ^ swz] = a0 * ir2; wp[3 ^ swz] = a1 * ir2; wp[4 ^ swz] = a2 * ir2;
-    wp[5 ^ swz] = b0 * ir2; wp[6 ^ swz] = b1 * ir2; wp[7 ^ swz] = b2 * ir2;
-    // camera row: e, then row a: f, u0, v0, t(3) = -a_X (:368-376), w(3); row b likewise
+    wp[2 ^ swz] = J.ax[0]; wp[3 ^ swz] = J.ax[1]; wp[4 ^ swz] = J.ax[2];
+    wp[5 ^ swz] = J.bx[0]; wp[6 ^ swz] = J.bx[1]; wp[7 ^ swz] = J.bx[2];
+    // camera row: e, then the nine entries of row a and of row b
     double* w = st + 256 + lane * 21;
     w[0] = e0; w[1] = e1;
-    w[2] = af * ir2; w[3] = au * ir2; w[4] = 0.0;
-    w[5] = -a0 * ir2; w[6] = -a1 * ir2; w[7] = -a2 * ir2;
-    w[8] = aw0 * ir2; w[9] = aw1 * ir2; w[10] = aw2 * ir2;
-    w[11] = bf * ir2; w[12] = 0.0; w[13] = au * ir2;
-    w[14] = -b0 * ir2; w[15] = -b1 * ir2; w[16] = -b2 * ir2;
-    w[17] = bw0 * ir2; w[18] = bw1 * ir2; w[19] = bw2 * ir2;
+#pragma unroll
+    for (int a = 0; a < 9; ++a) {
+      w[2 + a] = J.ja[a];
+      w[11 + a] = J.jb[a];
+    }
     }
     __syncwarp();
     {
@@ -255,7 +229,10 @@ int launch_cost(ba_engine* e, int which, int slot, cudaStream_t s) {
   return BA_OK;
 }
 
-int launch_k1(ba_engine* e, cudaStream_t s, bool conditional) {
+// Dense matrix-free scenes (dense_matrix_free) never read JP / JC back -- K2a, the camera blocks,
+// K2b and the point update re-derive the rows -- so only the camera table is refreshed; `force_rows`
+// writes them all the same (ba_buffer_read of JP / JC: tests, diagnostics).
+int launch_k1(ba_engine* e, cudaStream_t s, bool conditional, bool force_rows) {
   const size_t tab_bytes = tab_smem_bytes(e);
   const size_t smem = tab_bytes + 8 * kK1Stage * sizeof(double);
   const double2* xy = reinterpret_cast<const double2*>(e->obs_xy);
@@ -268,6 +245,7 @@ int launch_k1(ba_engine* e, cudaStream_t s, bool conditional) {
                                                         e->camtab[0], ctl);
     BA_LAUNCH_CHECK();
   }
+  if (dense_matrix_free(e) && !force_rows) return BA_OK;
 #define BA_K1_LAUNCH(D, T)                                                                     \
   do {                                                                                         \
     if (smem > 48 * 1024)                                                                      \

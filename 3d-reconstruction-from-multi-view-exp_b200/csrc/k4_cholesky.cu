@@ -270,19 +270,19 @@ __device__ __forceinline__ void panel_product(const double* __restrict__ A, cons
   }
 }
 
-__global__ void __launch_bounds__(kPanelThreads)
-chol_step_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int p_blocks,
-                 double* __restrict__ Lt, const double* __restrict__ Lp, double* __restrict__ W,
-                 ba_lm_state* ctl, int use_ctl) {
-  if (use_ctl && ctl->done) return;
-  extern __shared__ double psm[];
+// One virtual block `vb` of step p (vb < p_blocks: panel block, else update tile vb - p_blocks).
+// S and Lp are read with ld.global.cg: in the persistent kernel below other SMs wrote them within the
+// same launch, and the L1 is not coherent.
+__device__ __forceinline__ void chol_step_body(int vb, double* S, int ld, int n_rows, int k0, int nb, int p_blocks,
+                                               double* Lt, const double* Lp, double* W, ba_lm_state* ctl,
+                                               double* psm) {
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  if ((int)blockIdx.x >= p_blocks) {
+  if (vb >= p_blocks) {
     // ---- update block: one 64 x 64 tile of the previous panel's trailing update ---------------
     double* sA = psm;              // [64][68] Lp[:, r0 ..]
     double* sB = psm + NB * kSLD;  // [64][68] Lp[:, c0 ..]
-    const int t = blockIdx.x - p_blocks;
+    const int t = vb - p_blocks;
     int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
     while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
     while (ti * (ti + 1) / 2 > t) --ti;
@@ -291,8 +291,8 @@ chol_step_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int
     const int r0 = t0 + ti * NB, c0 = t0 + tj * NB;
     for (int q = tid; q < NB * NB; q += kPanelThreads) {
       const int m = q >> 6, x = q & 63;
-      sA[m * kSLD + x] = r0 + x < n_rows ? Lp[(size_t)m * ld + r0 + x] : 0.0;
-      sB[m * kSLD + x] = c0 + x < n_rows ? Lp[(size_t)m * ld + c0 + x] : 0.0;
+      sA[m * kSLD + x] = r0 + x < n_rows ? __ldcg(Lp + (size_t)m * ld + r0 + x) : 0.0;
+      sB[m * kSLD + x] = c0 + x < n_rows ? __ldcg(Lp + (size_t)m * ld + c0 + x) : 0.0;
     }
     __syncthreads();
     const int rb = warp >> 2, cb = warp & 3;  // 16 x 16 sub-tile per warp
@@ -306,8 +306,8 @@ chol_step_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int
         const int r = r0 + rb * 16 + (lane >> 2) + 8 * i, c = c0 + cb * 16 + 2 * (lane & 3) + 8 * j;
         if (r >= n_rows || c > r) continue;
         double* dst = S + (size_t)r * ld + c;
-        dst[0] -= acc[i][j][0];
-        if (c + 1 <= r) dst[1] -= acc[i][j][1];
+        dst[0] = __ldcg(dst) - acc[i][j][0];
+        if (c + 1 <= r) dst[1] = __ldcg(dst + 1) - acc[i][j][1];
       }
     return;
   }
@@ -318,7 +318,7 @@ chol_step_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int
   double* sB = piv + NB;                  // [64][68] Lp[:, k0 ..]   (previous panel, k-major)
   double* sA = sB + NB * kSLD;            // [64][68] Lp[:, rbase ..]
   __shared__ int s_fail;
-  const int rbase = k0 + nb + ((int)blockIdx.x - 1) * NB;
+  const int rbase = k0 + nb + (vb - 1) * NB;
   if (tid == 0) s_fail = kNoBadPivot;
   {
     double vd[8], va[8];
@@ -327,16 +327,16 @@ chol_step_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int
     for (int u = 0; u < 8; ++u) {
       const int r = (tid >> 6) + 8 * u;
       vd[u] = (r == c) ? 1.0 : 0.0;
-      if (r < nb && c <= r) vd[u] = S[(size_t)(k0 + r) * ld + k0 + c];
-      va[u] = (blockIdx.x == 0 && r == c) ? 1.0 : 0.0;
-      if (blockIdx.x != 0 && rbase + r < n_rows && c < nb) va[u] = S[(size_t)(rbase + r) * ld + k0 + c];
+      if (r < nb && c <= r) vd[u] = __ldcg(S + (size_t)(k0 + r) * ld + k0 + c);
+      va[u] = (vb == 0 && r == c) ? 1.0 : 0.0;
+      if (vb != 0 && rbase + r < n_rows && c < nb) va[u] = __ldcg(S + (size_t)(rbase + r) * ld + k0 + c);
     }
     if (Lp) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int m = (tid >> 6) + 8 * u;
-        sB[m * kSLD + c] = k0 + c < n_rows ? Lp[(size_t)m * ld + k0 + c] : 0.0;
-        sA[m * kSLD + c] = (blockIdx.x != 0 && rbase + c < n_rows) ? Lp[(size_t)m * ld + rbase + c] : 0.0;
+        sB[m * kSLD + c] = k0 + c < n_rows ? __ldcg(Lp + (size_t)m * ld + k0 + c) : 0.0;
+        sA[m * kSLD + c] = (vb != 0 && rbase + c < n_rows) ? __ldcg(Lp + (size_t)m * ld + rbase + c) : 0.0;
       }
     }
 #pragma unroll
@@ -351,7 +351,7 @@ chol_step_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int
     // previous panel's update of this slice: warp -> 16 rows x 32 columns of the 128 x 64 slice
     const int rb = warp >> 1, ch = warp & 1;
     const bool own = rb >= 4;  // rows 64..127 = this block's rows, else the diagonal block
-    if (!(own && blockIdx.x == 0)) {
+    if (!(own && vb == 0)) {
       double acc[2][4][2] = {};
       panel_product<2, 4>(own ? sA : sB, sB, (own ? rb - 4 : rb) * 16 + (lane >> 2), ch * 32 + (lane >> 2),
                           lane & 3, acc);
@@ -375,12 +375,17 @@ chol_step_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int
   double a[kPanelCols];
 #pragma unroll
   for (int j = 0; j < kPanelCols; ++j) a[j] = T[r][kPanelCols * cg + j];
+  // Look-ahead: the thread that owns column k + 1 updates that entry first and publishes it (into the
+  // other column buffer) BEFORE its remaining FMAs of step k, so the next step's column is on its way
+  // while the bulk of this step's update runs; the barrier of step k + 1 then waits for arithmetic only.
+  // Every entry still receives the same FMAs in the same order: the factor is bit-identical.
+  if (cg == 0) col[r] = a[0];
   for (int g = 0; g < NB / kPanelCols; ++g) {
 #pragma unroll
     for (int kk = 0; kk < kPanelCols; ++kk) {
       const int k = kPanelCols * g + kk;
       double* ck = col + (kk & 1) * (2 * NB);
-      if (cg == g) ck[r] = a[kk];
+      double* cn = col + ((kk + 1) & 1) * (2 * NB);
       __syncthreads();
       if (cg >= g) {
         const double d = ck[k];
@@ -393,6 +398,7 @@ chol_step_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int
             const double2 cv = pr[jp];
             a[2 * jp] = fma(-la, cv.x, a[2 * jp]);
             a[2 * jp + 1] = fma(-la, cv.y, a[2 * jp + 1]);
+            if (jp == 0 && kk == kPanelCols - 1 && cg == g + 1) cn[r] = a[0];
           }
         } else {
 #pragma unroll
@@ -401,6 +407,7 @@ chol_step_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int
               const double2 cv = pr[jp];
               if (2 * jp > kk) a[2 * jp] = fma(-la, cv.x, a[2 * jp]);
               a[2 * jp + 1] = fma(-la, cv.y, a[2 * jp + 1]);
+              if (kk + 1 < kPanelCols && jp == (kk + 1) / 2) cn[r] = a[kk + 1];
             }
           }
         }
@@ -418,7 +425,7 @@ chol_step_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int
   __syncthreads();
   for (int q = tid; q < 2 * NB * NB; q += kPanelThreads) T[q >> 6][q & 63] *= piv[q & 63];
   __syncthreads();
-  if (blockIdx.x == 0) {
+  if (vb == 0) {
     if (tid == 0) report_bad_pivot(ctl, s_fail);
     for (int q = tid; q < NB * NB; q += kPanelThreads) {
       const int m = q >> 6, rr = q & 63;
@@ -435,6 +442,15 @@ chol_step_kernel(double* __restrict__ S, int ld, int n_rows, int k0, int nb, int
       if (rbase + rr < n_rows && c < nb) Lt[(size_t)c * ld + rbase + rr] = T[NB + rr][c];
     }
   }
+}
+
+
+__global__ void __launch_bounds__(kPanelThreads)
+chol_step_kernel(double* S, int ld, int n_rows, int k0, int nb, int p_blocks, double* Lt, const double* Lp,
+                 double* W, ba_lm_state* ctl, int use_ctl) {
+  if (use_ctl && ctl->done) return;
+  extern __shared__ double psm[];
+  chol_step_body((int)blockIdx.x, S, ld, n_rows, k0, nb, p_blocks, Lt, Lp, W, ctl, psm);
 }
 
 // Back substitution L^T x = y (y = row rhs_row of the factor) by 64-column blocks from the
@@ -537,6 +553,55 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
   __syncthreads();
 }
 
+// ---- small systems: the whole factorisation in ONE persistent launch ------------------------------
+// The chain of chol_step_kernel launches (one per 64-column panel) spends a third of its time between
+// kernels: launch, drain, the first loads of the next launch (C3, n = 1793: 29 launches, 0.62 ms).
+// chol_fused_kernel runs the same steps -- the same virtual blocks, the same arithmetic in the same
+// order, so the factor is bit-identical -- inside one cooperative launch, with a grid barrier where a
+// launch boundary was.  Panel blocks go to the first CTAs; the update tiles of the previous panel,
+// which nothing in the step waits for, are dealt to the CTAs that hold no panel block, so that the
+// CTAs on the critical path (slice update, elimination) reach the barrier first.
+__global__ void __launch_bounds__(kPanelThreads)
+chol_fused_kernel(double* S, int ld, int n, int n_rows, double* Lt, double* Winv, unsigned int* bar,
+                  ba_lm_state* ctl, int use_ctl) {
+  if (use_ctl && ctl->done) return;
+  extern __shared__ double psm[];
+  const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+  unsigned int epoch = 0;
+  int panel = 0;
+  for (int k0 = 0; k0 < n; k0 += NB, ++panel) {
+    const int nb = n - k0 < NB ? n - k0 : NB;
+    const int below = n_rows - (k0 + nb);
+    const int p_blocks = 1 + (below + NB - 1) / NB;
+    int u_blocks = 0;
+    if (panel > 0) {
+      const int rest = n_rows - (k0 + NB);  // rows / columns beyond block column `panel`
+      if (rest > 0) {
+        const int nt = (rest + NB - 1) / NB;
+        u_blocks = nt * (nt + 1) / 2;
+      }
+    }
+    double* Lt_cur = Lt + (size_t)(panel & 1) * NB * ld;
+    const double* Lt_prev = panel > 0 ? Lt + (size_t)((panel - 1) & 1) * NB * ld : nullptr;
+    double* W = Winv + (size_t)panel * NB * NB;
+    for (int vb = cta; vb < p_blocks; vb += G) {
+      chol_step_body(vb, S, ld, n_rows, k0, nb, p_blocks, Lt_cur, Lt_prev, W, ctl, psm);
+      __syncthreads();
+    }
+    if (u_blocks > 0) {
+      const bool spare = G > p_blocks;  // CTAs without a panel block take all the tiles
+      const int first = spare ? cta - p_blocks : cta;
+      const int stride = spare ? G - p_blocks : G;
+      if (first >= 0)
+        for (int t = first; t < u_blocks; t += stride) {
+          chol_step_body(p_blocks + t, S, ld, n_rows, k0, nb, p_blocks, Lt_cur, Lt_prev, W, ctl, psm);
+          __syncthreads();
+        }
+    }
+    if (k0 + NB < n) grid_barrier(bar, ++epoch * (unsigned int)G, ctl);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 chol_backsolve_grid_kernel(const double* __restrict__ S, int ld, int n, int rhs_row,
                            const double* __restrict__ W, double* __restrict__ ywork,
@@ -627,6 +692,41 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
     // small systems: one launch per panel, the previous panel's update rides along
     constexpr size_t kStepSmem = (2 * NB * (NB + 1) + 5 * NB + 2 * NB * kSLD) * sizeof(double);
     BA_CUDA(cudaFuncSetAttribute(chol_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStepSmem));
+    static const bool no_persist = std::getenv("BA_CHOL_NO_PERSIST") != nullptr;  // A/B timing: one launch per panel
+    if (!no_persist) {
+      BA_CUDA(cudaFuncSetAttribute(chol_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStepSmem));
+      // grid: enough CTAs for the busiest step (panel blocks + the tiles of the previous panel's update)
+      int want = 1;
+      {
+        int panel = 0;
+        for (int k0 = 0; k0 < n; k0 += NB, ++panel) {
+          const int nb = n - k0 < NB ? n - k0 : NB;
+          const int below = n_rows - (k0 + nb);
+          int blocks = 1 + (below + NB - 1) / NB;
+          const int rest = n_rows - (k0 + NB);
+          if (panel > 0 && rest > 0) {
+            const int nt = (rest + NB - 1) / NB;
+            blocks += nt * (nt + 1) / 2;
+          }
+          if (blocks > want) want = blocks;
+        }
+      }
+      const int G = want < e->num_sms ? want : e->num_sms;
+      BA_CUDA(cudaMemsetAsync(e->chol_bar, 0, sizeof(unsigned int), s));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(G);
+      cfg.blockDim = dim3(kPanelThreads);
+      cfg.dynamicSmemBytes = kStepSmem;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      BA_CUDA(cudaLaunchKernelEx(&cfg, chol_fused_kernel, e->P(), ld, n, n_rows, e->Lt, e->Winv, e->chol_bar, e->ctl,
+                                 use_ctl));
+      BA_LAUNCH_CHECK();
+    } else {
     int panel = 0;
     for (int k0 = 0; k0 < n; k0 += NB, ++panel) {
       const int nb = n - k0 < NB ? n - k0 : NB;
@@ -645,6 +745,7 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
       chol_step_kernel<<<p_blocks + u_blocks, kPanelThreads, kStepSmem, s>>>(
           e->P(), ld, n_rows, k0, nb, p_blocks, Lt_cur, Lt_prev, e->Winv + (size_t)panel * NB * NB, e->ctl, use_ctl);
       BA_LAUNCH_CHECK();
+    }
     }
   } else {
   int panel = 0;
@@ -685,7 +786,8 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
     }
   }
   }
-  if (n >= 2048 && !std::getenv("BA_CHOL_BACKSOLVE_1CTA")) {
+  static const int grid_min = std::getenv("BA_CHOL_BACKSOLVE_GRID_MIN") ? std::atoi(std::getenv("BA_CHOL_BACKSOLVE_GRID_MIN")) : 2048;
+  if (n >= grid_min && !std::getenv("BA_CHOL_BACKSOLVE_1CTA")) {
     const int nblk = (n + NB - 1) / NB;
     const int G = nblk < e->num_sms ? nblk : e->num_sms;
     BA_CUDA(cudaMemsetAsync(e->chol_bar, 0, sizeof(unsigned int), s));

@@ -106,7 +106,11 @@ __global__ void camera_update_kernel(int M, double f0, const double* __restrict_
 }
 
 // ---- point back-substitution + trial cost (:152, :155, :159-162) -------------------------------
-template <bool DENSE>
+// MF (dense scenes, see dense_matrix_free): Y is not read back (216 B per observation) but re-derived
+// from the camera table of the linearisation state, X_j and L_j^-1 with the arithmetic K2b wrote it
+// with (obs_jacobian, scaled_point_rows, y_entry: the same bits, so the step is the same step);
+// both camera tables and the camera step sit in shared memory.
+template <bool DENSE, bool MF>
 __global__ void __launch_bounds__(256)
 point_update_cost_kernel(int64_t N, int M, const int64_t* __restrict__ obs_ptr,
                          const int32_t* __restrict__ obs_cam, const double2* __restrict__ xy,
@@ -114,9 +118,23 @@ point_update_cost_kernel(int64_t N, int M, const int64_t* __restrict__ obs_ptr,
                          const double* __restrict__ Z, const double* __restrict__ LINV,
                          const double* __restrict__ dxi, const double* __restrict__ X,
                          double* __restrict__ X2, const double* __restrict__ tab2, double f0,
-                         double* __restrict__ cost_part, const ba_lm_state* ctl, int use_ctl) {
+                         double* __restrict__ cost_part, const ba_lm_state* ctl, int use_ctl,
+                         const double* __restrict__ tab0, int axis) {
+  static_assert(DENSE || !MF, "the matrix-free variant is the dense one");
   if (use_ctl && ctl->done) return;
   __shared__ double scratch[32];
+  extern __shared__ double pu_smem[];  // MF: [table of the linearisation state | trial table | dxi]
+  double* s_tab0 = pu_smem;
+  double* s_tab2 = pu_smem + (MF ? tab_smem_doubles(M) : 0);
+  double* s_dxi = s_tab2 + (MF ? tab_smem_doubles(M) : 0);
+  if (MF) {
+    for (int k = threadIdx.x; k < M * kCamTab; k += blockDim.x) {
+      s_tab0[(k >> 4) * kTabStride + (k & 15)] = tab0[k];
+      s_tab2[(k >> 4) * kTabStride + (k & 15)] = tab2[k];
+    }
+    for (int k = threadIdx.x; k < 9 * M; k += blockDim.x) s_dxi[k] = dxi[k];
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -124,7 +142,30 @@ point_update_cost_kernel(int64_t N, int M, const int64_t* __restrict__ obs_ptr,
   for (int64_t j = warp; j < N; j += nwarps) {
     const int64_t lo = DENSE ? j * M : obs_ptr[j];
     const int64_t hi = DENSE ? lo + M : obs_ptr[j + 1];
+    const double* m = LINV + 6 * (size_t)j;
     double s0 = 0, s1 = 0, s2 = 0;
+    if (MF) {
+      const double xj0 = X[3 * j], xj1 = X[3 * j + 1], xj2 = X[3 * j + 2];
+      const double m00 = m[0], m10 = m[1], m11 = m[2], m20 = m[3], m21 = m[4], m22 = m[5];
+      for (int64_t o = lo + lane; o < hi; o += 32) {
+        const int i = (int)(o - lo);
+        const uint32_t mask = gauge_mask(i, axis);
+        ObsJacobian J;
+        obs_jacobian(s_tab0 + (size_t)i * kTabStride, xj0, xj1, xj2, f0, J);
+        double ta[3], tb[3];
+        scaled_point_rows(J.ax, J.bx, m00, m10, m11, m20, m21, m22, ta, tb);
+        const double* d = s_dxi + 9 * i;
+#pragma unroll
+        for (int a = 0; a < 9; ++a) {
+          const bool pin = (mask >> a) & 1u;
+          const double ja = pin ? 0.0 : J.ja[a], jb = pin ? 0.0 : J.jb[a];
+          const double da = d[a];
+          s0 = fma(y_entry(ja, jb, ta[0], tb[0]), da, s0);
+          s1 = fma(y_entry(ja, jb, ta[1], tb[1]), da, s1);
+          s2 = fma(y_entry(ja, jb, ta[2], tb[2]), da, s2);
+        }
+      }
+    } else {
     for (int64_t o = lo + lane; o < hi; o += 32) {
       const int i = DENSE ? (int)(o - lo) : obs_cam[o];
       const double* d = dxi + 9 * (size_t)i;
@@ -133,26 +174,26 @@ point_update_cost_kernel(int64_t N, int M, const int64_t* __restrict__ obs_ptr,
 #pragma unroll
         for (int a = 0; a < 9; ++a) {
           const double da = d[a];
-          s0 += y0[a] * da;
-          s1 += y0[ld + a] * da;
-          s2 += y0[2 * (size_t)ld + a] * da;
+          s0 = fma(y0[a], da, s0);
+          s1 = fma(y0[ld + a], da, s1);
+          s2 = fma(y0[2 * (size_t)ld + a], da, s2);
         }
       } else {
         const double* y = Ysp + (size_t)o * 27;
 #pragma unroll
         for (int a = 0; a < 9; ++a) {
           const double da = d[a];
-          s0 += y[a] * da;
-          s1 += y[9 + a] * da;
-          s2 += y[18 + a] * da;
+          s0 = fma(y[a], da, s0);
+          s1 = fma(y[9 + a], da, s1);
+          s2 = fma(y[18 + a], da, s2);
         }
       }
+    }
     }
     s0 = warp_sum(s0) + Z[3 * j];
     s1 = warp_sum(s1) + Z[3 * j + 1];
     s2 = warp_sum(s2) + Z[3 * j + 2];
     // dX = -L^-T v with m = L^-1 (lower): (L^-T v)[b] = sum_{d >= b} m[d][b] v[d]
-    const double* m = LINV + 6 * (size_t)j;
     const double x0 = X[3 * j] - (m[0] * s0 + m[1] * s1 + m[3] * s2);
     const double x1 = X[3 * j + 1] - (m[2] * s1 + m[4] * s2);
     const double x2 = X[3 * j + 2] - (m[5] * s2);
@@ -161,7 +202,7 @@ point_update_cost_kernel(int64_t N, int M, const int64_t* __restrict__ obs_ptr,
     }
     for (int64_t o = lo + lane; o < hi; o += 32) {
       const int i = DENSE ? (int)(o - lo) : obs_cam[o];
-      const double* T = tab2 + (size_t)i * kCamTab;
+      const double* T = MF ? s_tab2 + (size_t)i * kTabStride : tab2 + (size_t)i * kCamTab;
       const double d0 = x0 - T[9], d1 = x1 - T[10], d2 = x2 - T[11];
       const double2 mm = xy[o];
       const double p = T[0] * d0 + T[1] * d1 + T[2] * d2;
@@ -199,14 +240,21 @@ int launch_update_trial(ba_engine* e, bool conditional, cudaStream_t s) {
   BA_LAUNCH_CHECK();
   const int grid = balanced_blocks((e->N + 7) / 8, (int64_t)e->num_sms * 8);  // 8 warps = 8 points per block
   const double2* xy = reinterpret_cast<const double2*>(e->obs_xy);
-  if (e->dense)
-    point_update_cost_kernel<true><<<grid, 256, 0, s>>>(
-        e->N, e->M, e->obs_ptr, e->obs_cam, xy, e->Yt, e->n_pad, e->Ysp, e->Z, e->LINV, e->dxi,
-        e->X[0], e->X[1], e->camtab[1], e->f0, e->cost_part, e->ctl, use_ctl);
-  else
-    point_update_cost_kernel<false><<<grid, 256, 0, s>>>(
-        e->N, e->M, e->obs_ptr, e->obs_cam, xy, e->Yt, e->n_pad, e->Ysp, e->Z, e->LINV, e->dxi,
-        e->X[0], e->X[1], e->camtab[1], e->f0, e->cost_part, e->ctl, use_ctl);
+  const bool mf = dense_matrix_free(e);
+  const size_t smem = mf ? (2 * tab_smem_doubles(e->M) + 9 * (size_t)e->M) * sizeof(double) : 0;
+#define BA_PU_LAUNCH(D, F)                                                                                       \
+  do {                                                                                                           \
+    if (smem > 48 * 1024)                                                                                        \
+      BA_CUDA(cudaFuncSetAttribute(point_update_cost_kernel<D, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                   (int)smem));                                                                  \
+    point_update_cost_kernel<D, F><<<grid, 256, smem, s>>>(                                                      \
+        e->N, e->M, e->obs_ptr, e->obs_cam, xy, e->Yt, e->n_pad, e->Ysp, e->Z, e->LINV, e->dxi, e->X[0], e->X[1], \
+        e->camtab[1], e->f0, e->cost_part, e->ctl, use_ctl, e->camtab[0], e->axis);                              \
+  } while (0)
+  if (mf) BA_PU_LAUNCH(true, true);
+  else if (e->dense) BA_PU_LAUNCH(true, false);
+  else BA_PU_LAUNCH(false, false);
+#undef BA_PU_LAUNCH
   BA_LAUNCH_CHECK();
   cost_finish2_kernel<<<1, 256, 0, s>>>(e->cost_part, grid, e->cost_buf + 1, e->ctl, use_ctl);
   BA_LAUNCH_CHECK();
