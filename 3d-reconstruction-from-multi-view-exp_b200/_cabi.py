@@ -89,6 +89,7 @@ SIGNATURES = {
     "ba_profile_reset": (C.c_int, [_P]),
     "ba_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "ba_syrk_feed": (C.c_int, []),
+    "ba_matrix_free": (C.c_int, [_P]),
     "ba_syrk_plan_info": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ba_projective_depth_primary": (C.c_int, [C.c_int, C.c_int64, C.c_int32, _P, C.c_double, C.c_double, C.c_int,

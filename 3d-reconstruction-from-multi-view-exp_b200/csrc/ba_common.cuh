@@ -266,29 +266,32 @@ __host__ __device__ constexpr size_t tab_smem_doubles(int M) { return ((size_t)M
 // compiler contraction), so all callers get the same bits.
 struct ObsJacobian {
   double p, q, r;       // projection before the division
+  double ir, inv_f0;    // 1 / r; 1 / f0 (from the table)
   double ax[3], bx[3];  // d e0 / dX, d e1 / dX                         = JP[2..4], JP[5..7]
   double ja[9], jb[9];  // d e0 / d(f, u0, v0, t, w), d e1 / d(...)     = JC[2..10], JC[11..19]
 };
-__device__ __forceinline__ void obs_jacobian(const double* T, double x0, double x1, double x2, double f0,
-                                             ObsJacobian& J) {
+// One division per observation (1 / r): the per-camera quotients 1 / f, u0 / f0, v0 / f0, 1 / f0 come
+// with the table row (cam_prep_kernel), and 1 / r^2 = (1 / r)^2.
+__device__ __forceinline__ void obs_jacobian(const double* T, double x0, double x1, double x2, ObsJacobian& J) {
   const double gp0 = T[0], gp1 = T[1], gp2 = T[2];
   const double gq0 = T[3], gq1 = T[4], gq2 = T[5];
   const double gr0 = T[6], gr1 = T[7], gr2 = T[8];
-  const double fi = T[12], u0 = T[13], v0 = T[14];
+  const double inv_f = T[12], uf = T[13], vf = T[14], inv_f0 = T[15];
   const double d0 = x0 - T[9], d1 = x1 - T[10], d2 = x2 - T[11];
   const double p = fma(gp2, d2, fma(gp1, d1, __dmul_rn(gp0, d0)));
   const double q = fma(gq2, d2, fma(gq1, d1, __dmul_rn(gq0, d0)));
   const double r = fma(gr2, d2, fma(gr1, d1, __dmul_rn(gr0, d0)));
-  J.p = p; J.q = q; J.r = r;
+  const double ir = 1.0 / r;
+  J.p = p; J.q = q; J.r = r; J.ir = ir; J.inv_f0 = inv_f0;
   // a_theta = r dp/dtheta - p dr/dtheta, b_theta = r dq/dtheta - q dr/dtheta; J = (a, b) / r^2
-  const double ir2 = 1.0 / __dmul_rn(r, r);
+  const double ir2 = __dmul_rn(ir, ir);
   const double a0 = fma(r, gp0, -__dmul_rn(p, gr0)), a1 = fma(r, gp1, -__dmul_rn(p, gr1)),
                a2 = fma(r, gp2, -__dmul_rn(p, gr2));  // :450
   const double b0 = fma(r, gq0, -__dmul_rn(q, gr0)), b1 = fma(r, gq1, -__dmul_rn(q, gr1)),
                b2 = fma(r, gq2, -__dmul_rn(q, gr2));  // :459
-  const double af = __dmul_rn(r, fma(-(u0 / f0), r, p) / fi);  // :336
-  const double bf = __dmul_rn(r, fma(-(v0 / f0), r, q) / fi);  // :337
-  const double au = __dmul_rn(r, r / f0);                      // :350-356
+  const double af = __dmul_rn(r, __dmul_rn(fma(-uf, r, p), inv_f));  // :336
+  const double bf = __dmul_rn(r, __dmul_rn(fma(-vf, r, q), inv_f));  // :337
+  const double au = __dmul_rn(r, __dmul_rn(r, inv_f0));              // :350-356
   // rotation: d(p, q, r) / dw = grad x (X - t) (:391-396)  =>  a_w = a_X x d, b_w = b_X x d
   const double aw0 = fma(a1, d2, -__dmul_rn(a2, d1)), aw1 = fma(a2, d0, -__dmul_rn(a0, d2)),
                aw2 = fma(a0, d1, -__dmul_rn(a1, d0));
@@ -304,6 +307,26 @@ __device__ __forceinline__ void obs_jacobian(const double* T, double x0, double 
   J.jb[3] = -J.bx[0]; J.jb[4] = -J.bx[1]; J.jb[5] = -J.bx[2];
   J.jb[6] = __dmul_rn(bw0, ir2); J.jb[7] = __dmul_rn(bw1, ir2); J.jb[8] = __dmul_rn(bw2, ir2);
 }
+// Squared reprojection residual of one observation (:666-677), the same residual expression as the
+// linearisation's (one division): cost kernels and the trial cost of the point update.
+__device__ __forceinline__ double obs_cost(const double* T, double x0, double x1, double x2, double mx, double my) {
+  const double d0 = x0 - T[9], d1 = x1 - T[10], d2 = x2 - T[11];
+  const double p = fma(T[2], d2, fma(T[1], d1, __dmul_rn(T[0], d0)));
+  const double q = fma(T[5], d2, fma(T[4], d1, __dmul_rn(T[3], d0)));
+  const double r = fma(T[8], d2, fma(T[7], d1, __dmul_rn(T[6], d0)));
+  const double ir = 1.0 / r, inv_f0 = T[15];
+  const double e0 = fma(p, ir, -__dmul_rn(mx, inv_f0));
+  const double e1 = fma(q, ir, -__dmul_rn(my, inv_f0));
+  return fma(e1, e1, __dmul_rn(e0, e0));
+}
+// residual of the linearisation (:445, :454): e = (p, q) / r - (x, y) / f0
+__device__ __forceinline__ void obs_residual(const ObsJacobian& J, double mx, double my, double& e0, double& e1) {
+  e0 = fma(J.p, J.ir, -__dmul_rn(mx, J.inv_f0));
+  e1 = fma(J.q, J.ir, -__dmul_rn(my, J.inv_f0));
+}
+#endif
+
+#ifdef __CUDACC__
 // T = 2 Jx L^-T (2 x 3) from the point-side rows and m = L^-1 (lower), and one entry of
 // Y = Jc^T T (reference :128-132 through the Cholesky factor): pinned like obs_jacobian, K2b writes
 // Y with these and the dense point update re-derives the same bits.

@@ -835,6 +835,7 @@ int ba_profile_reset(ba_engine* e) {
 int ba_fp64_peak(int device, int use_dmma, double* tflops) { return fp64_peak(device, use_dmma, tflops); }
 
 int ba_syrk_feed(void) { return syrk_feed_is_tma(); }
+int ba_matrix_free(ba_engine* e) { return e && dense_matrix_free(e) ? 1 : 0; }
 
 int ba_syrk_plan_info(int n_cams, int64_t n_points, int tile, int num_sms, int* n_items, int* n_tiles,
                       double* makespan_rows, double* ideal_rows) {

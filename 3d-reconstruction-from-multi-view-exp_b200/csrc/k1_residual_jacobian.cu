@@ -16,7 +16,7 @@
 namespace ba {
 
 // ---- per-camera derived table -----------------------------------------------------------
-// row: gp(3) gq(3) gr(3) t(3) f u0 v0 pad, with gp = f R[:,0] + u0 R[:,2] etc. = rows of
+// row: gp(3) gq(3) gr(3) t(3) 1/f u0/f0 v0/f0 1/f0, with gp = f R[:,0] + u0 R[:,2] etc. = rows of
 // K R^T (:283-302); p = gp . (X - t) reproduces P [X;1] with P[:, 3] = -K R^T t.
 __global__ void cam_prep_kernel(int M, const double* __restrict__ f, const double* __restrict__ u,
                                 const double* __restrict__ R, const double* __restrict__ t,
@@ -35,10 +35,12 @@ __global__ void cam_prep_kernel(int M, const double* __restrict__ f, const doubl
     T[6 + k] = f0 * r2;
     T[9 + k] = t[3 * i + k];
   }
-  T[12] = fi;
-  T[13] = u0;
-  T[14] = v0;
-  T[15] = 0.0;
+  // per-camera quotients of the Jacobian formulas (:336-356), so that no kernel divides by them per
+  // observation: 1 / f, u0 / f0, v0 / f0, 1 / f0
+  T[12] = 1.0 / fi;
+  T[13] = u0 / f0;
+  T[14] = v0 / f0;
+  T[15] = 1.0 / f0;
 }
 
 int launch_cam_prep(ba_engine* e, int which, cudaStream_t s) {
@@ -100,11 +102,11 @@ k1_residual_jacobian_kernel(int64_t nobs, int M, const int32_t* __restrict__ obs
       j = obs_pt[o];
     }
     ObsJacobian J;
-    obs_jacobian(tab + (size_t)i * TS, X[3 * (size_t)j + 0], X[3 * (size_t)j + 1], X[3 * (size_t)j + 2], f0, J);
+    obs_jacobian(tab + (size_t)i * TS, X[3 * (size_t)j + 0], X[3 * (size_t)j + 1], X[3 * (size_t)j + 2], J);
     const double2 m = xy[o];
-    const double e0 = J.p / J.r - m.x / f0;  // :445
-    const double e1 = J.q / J.r - m.y / f0;  // :454
-    acc += e0 * e0 + e1 * e1;
+    double e0, e1;
+    obs_residual(J, m.x, m.y, e0, e1);  // :445, :454
+    acc += fma(e1, e1, __dmul_rn(e0, e0));
 
     double* wp = st + lane * 8;
     wp[0 ^ swz] = e0; wp[1 ^ swz] = e1;
@@ -169,17 +171,8 @@ cost_kernel(int64_t nobs, int M, const int32_t* __restrict__ obs_cam,
       i = obs_cam[o];
       j = obs_pt[o];
     }
-    const double* T = tab + (size_t)i * TS;
-    const double d0 = X[3 * (size_t)j + 0] - T[9];
-    const double d1 = X[3 * (size_t)j + 1] - T[10];
-    const double d2 = X[3 * (size_t)j + 2] - T[11];
     const double2 m = xy[o];
-    const double p = T[0] * d0 + T[1] * d1 + T[2] * d2;
-    const double q = T[3] * d0 + T[4] * d1 + T[5] * d2;
-    const double r = T[6] * d0 + T[7] * d1 + T[8] * d2;
-    const double e0 = p / r - m.x / f0;
-    const double e1 = q / r - m.y / f0;
-    acc += e0 * e0 + e1 * e1;
+    acc += obs_cost(tab + (size_t)i * TS, X[3 * (size_t)j + 0], X[3 * (size_t)j + 1], X[3 * (size_t)j + 2], m.x, m.y);
   }
   const double tot = block_sum(acc, scratch);
   if (threadIdx.x == 0) cost_part[blockIdx.x] = tot;

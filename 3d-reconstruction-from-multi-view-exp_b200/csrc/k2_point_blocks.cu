@@ -53,10 +53,9 @@ k2a_point_blocks_kernel(int64_t N, int M, const int64_t* __restrict__ obs_ptr,
       double e0, e1, a0, a1, a2, b0, b1, b2;
       if (MF) {
         ObsJacobian J;
-        obs_jacobian(k2a_tab + (size_t)(o - lo) * kTabStride, xj0, xj1, xj2, f0, J);
+        obs_jacobian(k2a_tab + (size_t)(o - lo) * kTabStride, xj0, xj1, xj2, J);
         const double2 m = xy[o];
-        e0 = J.p / J.r - m.x / f0;  // :445, as K1
-        e1 = J.q / J.r - m.y / f0;  // :454
+        obs_residual(J, m.x, m.y, e0, e1);  // :445, :454, as K1
         a0 = J.ax[0]; a1 = J.ax[1]; a2 = J.ax[2];
         b0 = J.bx[0]; b1 = J.bx[1]; b2 = J.bx[2];
       } else {
@@ -110,7 +109,7 @@ int launch_k2a(ba_engine* e, cudaStream_t s, bool conditional) {
 // MF (dense_matrix_free): the camera-side rows and the residual are re-derived (the block's camera
 // table row in registers, X_q and the observed point read per observation: 40 B instead of 160 B).
 template <bool DENSE, bool MF>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, MF ? 3 : 1)
 camera_blocks_kernel(int64_t N, int M, const int64_t* __restrict__ cam_ptr,
                      const int32_t* __restrict__ cm_perm, const double* __restrict__ JC,
                      double* __restrict__ Upart, const ba_lm_state* ctl,
@@ -139,10 +138,9 @@ camera_blocks_kernel(int64_t N, int M, const int64_t* __restrict__ cam_ptr,
     double v[kJC];
     if (MF) {
       ObsJacobian J;
-      obs_jacobian(T, X[3 * (size_t)q], X[3 * (size_t)q + 1], X[3 * (size_t)q + 2], f0, J);
+      obs_jacobian(T, X[3 * (size_t)q], X[3 * (size_t)q + 1], X[3 * (size_t)q + 2], J);
       const double2 m = xy[o];
-      v[0] = J.p / J.r - m.x / f0;  // :445, as K1
-      v[1] = J.q / J.r - m.y / f0;  // :454
+      obs_residual(J, m.x, m.y, v[0], v[1]);  // :445, :454, as K1
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
         v[2 + k] = J.ja[k];
@@ -329,7 +327,7 @@ k2b_point_solve_kernel(int64_t N, int M, int axis, const int64_t* __restrict__ o
         double a0, a1, a2, b0, b1, b2;
         if (MF) {
           ObsJacobian J;
-          obs_jacobian(tab + (size_t)i * kTabStride, xj0, xj1, xj2, f0, J);
+          obs_jacobian(tab + (size_t)i * kTabStride, xj0, xj1, xj2, J);
           a0 = J.ax[0]; a1 = J.ax[1]; a2 = J.ax[2];
           b0 = J.bx[0]; b1 = J.bx[1]; b2 = J.bx[2];
 #pragma unroll

@@ -144,13 +144,7 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
     const double v = camtab[(size_t)(which ? k : i) * kCamTab + c];
     sm.cam[which][c] = v;
     __syncwarp();
-    if (c == 0) {
-      const double f = sm.cam[which][12], u0 = sm.cam[which][13], v0 = sm.cam[which][14];
-      sm.cam[which][16] = 1.0 / f;
-      sm.cam[which][17] = u0 / f0;
-      sm.cam[which][18] = v0 / f0;
-      sm.cam[which][19] = 1.0 / f0;
-    }
+    if (c >= 12) sm.cam[which][c + 4] = v;  // 1 / f, u0 / f0, v0 / f0, 1 / f0 (cam_prep_kernel) where side_jacobian reads them
     __syncwarp();
   }
 
@@ -429,13 +423,7 @@ schur_pairs_reg_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__
     const double v = camtab[(size_t)(which ? k : i) * kCamTab + c];
     sm.cam[which][c] = v;
     __syncwarp();
-    if (c == 0) {
-      const double f = sm.cam[which][12], u0 = sm.cam[which][13], v0 = sm.cam[which][14];
-      sm.cam[which][16] = 1.0 / f;
-      sm.cam[which][17] = u0 / f0;
-      sm.cam[which][18] = v0 / f0;
-      sm.cam[which][19] = 1.0 / f0;
-    }
+    if (c >= 12) sm.cam[which][c + 4] = v;  // 1 / f, u0 / f0, v0 / f0, 1 / f0 (cam_prep_kernel) where side_jacobian reads them
     __syncwarp();
   }
 

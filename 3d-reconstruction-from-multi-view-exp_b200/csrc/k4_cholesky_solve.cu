@@ -102,7 +102,7 @@ __global__ void camera_update_kernel(int M, double f0, const double* __restrict_
     T[6 + k] = f0 * Rn[3 * k + 2];
   }
   T[9] = t0; T[10] = t1; T[11] = t2v;
-  T[12] = fi; T[13] = u0; T[14] = v0; T[15] = 0.0;
+  T[12] = 1.0 / fi; T[13] = u0 / f0; T[14] = v0 / f0; T[15] = 1.0 / f0;  // as cam_prep_kernel
 }
 
 // ---- point back-substitution + trial cost (:152, :155, :159-162) -------------------------------
@@ -151,7 +151,7 @@ point_update_cost_kernel(int64_t N, int M, const int64_t* __restrict__ obs_ptr,
         const int i = (int)(o - lo);
         const uint32_t mask = gauge_mask(i, axis);
         ObsJacobian J;
-        obs_jacobian(s_tab0 + (size_t)i * kTabStride, xj0, xj1, xj2, f0, J);
+        obs_jacobian(s_tab0 + (size_t)i * kTabStride, xj0, xj1, xj2, J);
         double ta[3], tb[3];
         scaled_point_rows(J.ax, J.bx, m00, m10, m11, m20, m21, m22, ta, tb);
         const double* d = s_dxi + 9 * i;
@@ -203,14 +203,8 @@ point_update_cost_kernel(int64_t N, int M, const int64_t* __restrict__ obs_ptr,
     for (int64_t o = lo + lane; o < hi; o += 32) {
       const int i = DENSE ? (int)(o - lo) : obs_cam[o];
       const double* T = MF ? s_tab2 + (size_t)i * kTabStride : tab2 + (size_t)i * kCamTab;
-      const double d0 = x0 - T[9], d1 = x1 - T[10], d2 = x2 - T[11];
       const double2 mm = xy[o];
-      const double p = T[0] * d0 + T[1] * d1 + T[2] * d2;
-      const double q = T[3] * d0 + T[4] * d1 + T[5] * d2;
-      const double r = T[6] * d0 + T[7] * d1 + T[8] * d2;
-      const double e0 = p / r - mm.x / f0;
-      const double e1 = q / r - mm.y / f0;
-      cost += e0 * e0 + e1 * e1;
+      cost += obs_cost(T, x0, x1, x2, mm.x, mm.y);
     }
   }
   const double tot = block_sum(cost, scratch);

@@ -302,6 +302,10 @@ class Engine:
     def profile_reset(self):
         _cabi.check(self._lib.ba_profile_reset(self._h))
 
+    def matrix_free(self) -> bool:
+        """Dense scene linearised matrix-free (Jacobian rows re-derived where they are used)."""
+        return bool(self._lib.ba_matrix_free(self._h))
+
     def profile(self) -> dict:
         out = {}
         for g in ("k1", "k2", "k3", "k4", "cost", "other", "syrk", "chol", "comm"):

@@ -588,7 +588,9 @@ def measure(ctx: Ctx, name: str, strong: bool, K: int, W: int, *, full_run_tol=N
             pass
         # memory-bound phases against the measured copy bandwidth (K1: 16 B read + 224 B written
         # per observation and linearisation)
-        if prof["k1"]["ms"] > 0:
+        out["linearisation"] = ("matrix-free: K2a, camera blocks, K2b and the point update re-derive the Jacobian "
+                                "rows; K1 stores nothing") if eng.matrix_free() else "K1 stores the Jacobian rows"
+        if prof["k1"]["ms"] > 0 and not eng.matrix_free():
             gbs = sc.nobs * 240.0 * K / (prof["k1"]["ms"] * 1e-3) / 1e9
             out["k1_hbm"] = {"achieved_gbs": gbs, "peak_gbs": hbm or 6650.0,
                              "peak_source": "MEASURED_PEAKS.json" if hbm else "fallback",

@@ -244,12 +244,19 @@ int ba_profile_enable(ba_engine* e, int on);
 int ba_profile_get(ba_engine* e, const char* group, double* total_ms, int64_t* launches);
 int ba_profile_reset(ba_engine* e);
 /* FP64 peak micro-benchmarks (register-resident loops): TFLOP/s.  use_dmma = 1: DMMA.8x8x4,
- * 0: DFMA, 2: both interleaved with equal FMA counts (do they share the FP64 datapath?). */
+ * 0: DFMA, 2: both interleaved with equal FMA counts (do they share the FP64 datapath?), 100 + w:
+ * the DFMA loop with w warps per SM (rate at low occupancy). */
 int ba_fp64_peak(int device, int use_dmma, double* tflops);
 /* How the 128-tile Schur SYRK / Cholesky trailing update gets its operands: 1 = TMA tensor copies +
  * mbarriers with a producer warp (cp.async.bulk.tensor, SASS UTMALDG), 0 = cp.async (LDGSTS; set
  * BA_SYRK_NO_TMA=1 for A/B timing, or the driver does not offer cuTensorMapEncodeTiled). */
 int ba_syrk_feed(void);
+/* 1 when this engine linearises matrix-free: a dense scene whose camera table fits shared memory
+ * (<= 361 cameras) re-derives the Jacobian rows in K2a, the camera blocks, K2b and the point update
+ * instead of storing them in K1 and reading them back (reference :309-427 evaluated where used);
+ * 0 otherwise (sparse visibility, more cameras, or BA_NO_MATRIX_FREE=1).  ba_buffer_read of the
+ * JP / JC rows still works: K1 writes them for that read. */
+int ba_matrix_free(ba_engine* e);
 /* Host-only (no device): plan the dense Schur product (K3) of an n_cams x n_points scene for a GPU
  * with num_sms SMs and `tile` = 64 or 128, verify that the work items cover every tile's K range
  * exactly once, and report the number of items / tiles and the modelled schedule length against

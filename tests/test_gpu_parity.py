@@ -145,6 +145,48 @@ def test_kernels_match_oracle_on_random_scenes(ba, n_cams, n_points, visibility,
     _check_one_linearisation(ba, obs, X, R, t, f, u, sc.f0, axis, dense=sc.dense)
 
 
+@pytest.mark.parametrize("n_cams,n_points,axis", [(30, 1500, "x-up_z-forward"), (120, 900, "x-right_z-forward"),
+                                                  (17, 333, "x-up_z-forward")])
+def test_matrix_free_linearisation_is_bitwise_the_stored_row_one(ba, n_cams, n_points, axis):
+    """A dense engine re-derives the Jacobian rows in K2a, the camera blocks, K2b and the point update
+    (ba_matrix_free); an engine built from the same observations as a LIST stores them in K1 and
+    reads them back.  The arithmetic is shared and pinned (obs_jacobian, scaled_point_rows, y_entry,
+    pair_accumulate in ba_common.cuh) and the summation orders coincide for full visibility, so
+    V, d_P, U, d_F, L^-1 and z must agree bit for bit -- as must the rows that the matrix-free engine
+    writes on request (JP / JC buffer reads)."""
+    sc = ba.scenes.make_scene(n_cams, n_points, seed=3 + n_cams, visibility=1.0, axis=axis)
+    assert sc.dense
+    obs = O.ObsList(sc.n_points, sc.n_cams, np.repeat(np.arange(sc.n_points), np.diff(sc.obs_ptr)),
+                    sc.obs_cam.astype(np.int64), sc.obs_xy, sc.obs_ptr)
+    X, R, t = O.normalize_gauge(sc.X0, sc.R0, sc.t0, axis)
+    f, u = sc.K0[:, 0, 0].copy(), sc.K0[:, :2, 2].copy()
+    mf = _engine_for(ba, obs, X, R, t, f, u, sc.f0, axis, dense=True)
+    st = _engine_for(ba, obs, X, R, t, f, u, sc.f0, axis, dense=False)
+    assert mf.matrix_free() and not st.matrix_free()
+    for eng in (mf, st):
+        eng.linearize()
+        eng.build_reduced(1e-3)
+    for name in ("V", "GPT", "U", "GCAM", "LINV", "Z", "JP", "JC"):
+        a, b = mf.buffer(name), st.buffer(name)
+        assert np.array_equal(a, b), f"{name}: {np.abs(a - b).max():.3e}"
+    # the reduced systems come from different Schur kernels (SYRK / pair products): equal to rounding;
+    # the dense engine keeps P = Y Y^T with the rhs in row 9M, the list engine the same layout
+    npad, n, rhs = mf.n_pad, mf.n_full, mf.rhs_row
+    assert (npad, n, rhs) == (st.n_pad, st.n_full, st.rhs_row)
+    Pa = mf.buffer("REDUCE")[: npad * npad].reshape(npad, npad)
+    Pb = st.buffer("REDUCE")[: npad * npad].reshape(npad, npad)
+    low = np.tril_indices(n)
+    _close(Pa[:n, :n][low], Pb[:n, :n][low], 1e-12, "P (lower triangle)")
+    _close(Pa[rhs, :n], Pb[rhs, :n], 1e-12, "rhs row")
+    # one step: the same trial state (the dense point update re-derives Y, the list one reads it)
+    for eng in (mf, st):
+        eng.solve_trial(1e-3)
+    for got, ref, what in zip(mf.get_state(1), st.get_state(1), ("X", "R", "t", "f", "u")):
+        _close(got, ref, 1e-11, f"trial {what}")
+    mf.close()
+    st.close()
+
+
 @pytest.mark.parametrize("name", RUN_CASES)
 @pytest.mark.parametrize("debug", [False, True])
 def test_full_run_matches_reference_golden(ba, name, debug):
