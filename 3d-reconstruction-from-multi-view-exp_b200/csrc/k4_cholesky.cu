@@ -15,9 +15,13 @@
 //                       W = L_D^-T for the back substitution (no serial solve there either).
 //                       Writes L rows in place and a k-major copy Lt for the update.
 //   chol_update_kernel  trailing update S -= L_panel L_panel^T on 64x64 tiles.
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "ba_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace ba {
 
@@ -634,13 +638,17 @@ chol_backsolve_grid_kernel(const double* __restrict__ S, int ld, int n, int rhs_
     if (tid < NB) yB[tid] = tid < w ? __ldcg(ywork + b0 + tid) : 0.0;
     __syncthreads();
     {
-      const int j = tid >> 2, p4 = tid & 3;  // x_B[j] = sum_c W[j][c] y_B[c]
-      const double* Wj = W + (size_t)blk * NB * NB + (size_t)j * NB + p4 * 16;
+      const int j = tid >> 2, p4 = tid & 3;  // x_B[j] = sum_c W[j][c] y_B[c]; columns 4 p4 + 16 m + {0..3}: coalesced
+      const double2* Wj = reinterpret_cast<const double2*>(W + (size_t)blk * NB * NB + (size_t)j * NB + p4 * 4);
       double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-      for (int c = 0; c < 16; c += 2) {
-        a0 = fma(Wj[c], yB[p4 * 16 + c], a0);
-        a1 = fma(Wj[c + 1], yB[p4 * 16 + c + 1], a1);
+      for (int m = 0; m < 4; ++m) {
+        const double2 lo = Wj[8 * m], hi = Wj[8 * m + 1];
+        const double* yq = yB + p4 * 4 + 16 * m;
+        a0 = fma(lo.x, yq[0], a0);
+        a1 = fma(lo.y, yq[1], a1);
+        a0 = fma(hi.x, yq[2], a0);
+        a1 = fma(hi.y, yq[3], a1);
       }
       double sx = a0 + a1;
       sx += __shfl_xor_sync(0xffffffffu, sx, 1);
@@ -665,6 +673,113 @@ chol_backsolve_grid_kernel(const double* __restrict__ S, int ld, int n, int rhs_
     }
     if (blk > 0) prefetch(blk - 1, cta);  // static data: in flight while the barrier is awaited
     if (blk > 0) grid_barrier(bar, ++epoch * G, ctl);
+  }
+}
+
+// ---- back substitution on one thread-block cluster (1024 <= n < 2048) ------------------------------
+// The single-block kernel streams the whole factor through one SM (C3, n = 1793: 12.9 MB, 0.21 ms --
+// a quarter of the factor + solve time); the grid-wide kernel pays a ~2 us software barrier and a
+// round trip through global memory for the running right-hand side per 64-block and is no faster at
+// this size.  Here eight CTAs form ONE CLUSTER: the running right-hand side lives in the shared
+// memory of the CTA that owns the chunk (chunk q belongs to CTA q % 8), the other CTAs read the
+// block they need through distributed shared memory, and the steps are separated by the hardware
+// cluster barrier.  Right-looking like the grid kernel: every CTA forms x_B = W_B y_B itself and
+// updates its own chunks; the factor rows and W of the next step are static and fetched before the
+// barrier.  Fixed summation order: deterministic.
+constexpr int kBsCluster = 8;
+constexpr int kBsMaxOwn = 4;  // chunks per CTA: n < 2048 -> at most 32 chunks
+
+__global__ void __launch_bounds__(256)
+chol_backsolve_cluster_kernel(const double* __restrict__ S, int ld, int n, int rhs_row,
+                              const double* __restrict__ W, double* __restrict__ dxi,
+                              const ba_lm_state* ctl, int use_ctl) {
+  if (use_ctl && ctl->done) return;  // the same answer in every CTA of the cluster
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cta = (int)cluster.block_rank(), G = (int)cluster.num_blocks();
+  __shared__ double ych[kBsMaxOwn][NB];  // running rhs of the chunks this CTA owns (chunk = cta + G * slot)
+  __shared__ double xB[NB], yB[NB], part[4][NB];
+  const int tid = threadIdx.x;
+  const int col = tid & 63, rg = tid >> 6;  // update: 64 columns x 4 groups of 16 rows
+  const int wj = tid >> 2, wp4 = tid & 3;   // x_B: row j, quarter p4 of the dot product
+  const int nblk = (n + NB - 1) / NB;
+  for (int slot = 0; slot < kBsMaxOwn; ++slot) {
+    const int q = cta + G * slot;
+    if (tid < NB) ych[slot][tid] = (q < nblk && q * NB + tid < n) ? S[(size_t)rhs_row * ld + q * NB + tid] : 0.0;
+  }
+  // static data of a step, fetched one step ahead: the rows of block `blk` over this CTA's chunks
+  // and this thread's piece of W_blk
+  double pre[kBsMaxOwn][16], wv[16];
+  auto prefetch = [&](int blk) {
+    const int b0 = blk * NB;
+#pragma unroll
+    for (int slot = 0; slot < kBsMaxOwn; ++slot) {
+      const int q = cta + G * slot;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int r = b0 + rg * 16 + u;
+        pre[slot][u] = (q < blk && r < n) ? S[(size_t)r * ld + q * NB + col] : 0.0;
+      }
+    }
+    // thread (j, p4) takes columns 4 p4 + 16 m + {0..3}: the four threads of a row read 64 contiguous
+    // bytes per m (with 16 consecutive columns per thread a warp-wide load touched 32 lines -- 4 us per
+    // 64-block, more than everything else in the step)
+    const double2* Wj = reinterpret_cast<const double2*>(W + (size_t)blk * NB * NB + (size_t)wj * NB + wp4 * 4);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const double2 lo = Wj[8 * m], hi = Wj[8 * m + 1];
+      wv[4 * m] = lo.x; wv[4 * m + 1] = lo.y; wv[4 * m + 2] = hi.x; wv[4 * m + 3] = hi.y;
+    }
+  };
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  prefetch(nblk - 1);
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  for (int blk = nblk - 1; blk >= 0; --blk) {
+    const int b0 = blk * NB;
+    const int w = n - b0 < NB ? n - b0 : NB;
+    {
+      const double* owner_y = cluster.map_shared_rank(&ych[0][0], blk % G);  // distributed shared memory
+      if (tid < NB) yB[tid] = owner_y[(blk / G) * NB + tid];
+    }
+    __syncthreads();
+    {
+      double a0 = 0.0, a1 = 0.0;  // x_B[j] = sum_c W[j][c] y_B[c]
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const double* yq = yB + wp4 * 4 + 16 * m;
+        a0 = fma(wv[4 * m], yq[0], a0);
+        a1 = fma(wv[4 * m + 1], yq[1], a1);
+        a0 = fma(wv[4 * m + 2], yq[2], a0);
+        a1 = fma(wv[4 * m + 3], yq[3], a1);
+      }
+      double sx = a0 + a1;
+      sx += __shfl_xor_sync(0xffffffffu, sx, 1);
+      sx += __shfl_xor_sync(0xffffffffu, sx, 2);
+      if (wp4 == 0) {
+        xB[wj] = sx;
+        if (blk % G == cta && wj < w) dxi[b0 + wj] = sx;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int slot = 0; slot < kBsMaxOwn; ++slot) {
+      const int q = cta + G * slot;
+      if (q < blk) {  // uniform in the CTA
+        double acc = 0.0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc = fma(pre[slot][u], xB[rg * 16 + u], acc);
+        part[rg][col] = acc;
+        __syncthreads();
+        if (rg == 0) ych[slot][col] -= (part[0][col] + part[1][col]) + (part[2][col] + part[3][col]);
+        __syncthreads();
+      }
+    }
+    // Split barrier: arrive (release: this step's updates of the running right-hand side) BEFORE the
+    // next step's loads are issued -- a release after them would wait for all of them to return --
+    // and wait after; the loads then overlap the barrier.
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    if (blk > 0) prefetch(blk - 1);
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
   }
 }
 
@@ -806,6 +921,25 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
     cfg.numAttrs = no_coop ? 0 : 1;
     BA_CUDA(cudaLaunchKernelEx(&cfg, chol_backsolve_grid_kernel, (const double*)e->P(), ld, n, e->rhs_row,
                                (const double*)e->Winv, e->ywork, e->dxi, e->chol_bar, e->ctl, use_ctl));
+    BA_LAUNCH_CHECK();
+    return BA_OK;
+  }
+  static const int cluster_min = std::getenv("BA_CHOL_BACKSOLVE_CLUSTER_MIN") ? std::atoi(std::getenv("BA_CHOL_BACKSOLVE_CLUSTER_MIN")) : 1024;  // measured: 7 blocks (C2) 8 us slower, 29 blocks (C3) 37 us faster than one CTA
+  if (n >= cluster_min && (n + NB - 1) / NB <= kBsCluster * kBsMaxOwn && !std::getenv("BA_CHOL_BACKSOLVE_1CTA")) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kBsCluster);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kBsCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    BA_CUDA(cudaLaunchKernelEx(&cfg, chol_backsolve_cluster_kernel, (const double*)e->P(), ld, n, e->rhs_row,
+                               (const double*)e->Winv, e->dxi, (const ba_lm_state*)e->ctl, use_ctl));
     BA_LAUNCH_CHECK();
     return BA_OK;
   }
