@@ -35,9 +35,8 @@
 
 namespace ba {
 
-constexpr int kPS = 14;            // register variant: doubles per point row in shared memory (112 B = 7 x 16: odd -> conflict-free LDS.128)
-constexpr int kPSD = 10;           // DMMA variant: 80 B = 5 x 16 (odd as well); the 9 doubles in use are the first 5 pieces
-constexpr int kPieces = 5;         // 16-byte pieces gathered per point row
+constexpr int kPS = 14;            // doubles per point row in shared memory (112 B = 7 x 16: odd -> conflict-free LDS.128)
+constexpr int kPieces = 5;         // register variant: 16-byte pieces gathered per point row (the 9 doubles in use)
 constexpr int kPairTile = 32;      // pairs are scheduled in kPairTile x kPairTile tiles of (i, k)
 constexpr int kDiagPart = 54;      // 45 unique entries of the diagonal block + 9 rhs entries
 constexpr int kQueue = 128;        // queue capacity (point ids)
@@ -94,7 +93,7 @@ __device__ __forceinline__ bool pair_from_linear(int64_t t, int M, int& i, int& 
 }
 
 struct PairSmem {
-  double stage[2][32 * kPSD];  // [stage][point of the round][kPS]: X (3), Vd^-1 (6: 00 01 02 11 12 22)
+  double stage[2][32 * kPS];  // [stage][point of the round][kPS]: X (3), Vd^-1 (6: 00 01 02 11 12 22)
   double cam[2][20];          // table rows of camera i and k (K1's layout) + 1/f, u0/f0, v0/f0, 1/f0
   double ifrag[2 * kFragX];   // [x][lane][8]: first 8 entries of Jc_i row x of the lane's point (DMMA A operand)
   double tfrag[2 * kFragX];   // [x][lane][8]: first 8 entries of row x of G Jc_k            (DMMA B operand)
@@ -176,7 +175,7 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
     double2* t1s = reinterpret_cast<double2*>(sm.tfrag + kFragX + lane * 8);
     const int sw = (lane >> 1) & 3;
     if (lane < cnt) {
-      const double* pt = sm.stage[st] + lane * kPSD;
+      const double* pt = sm.stage[st] + lane * kPS;
       const double2 x01 = *reinterpret_cast<const double2*>(pt);
       const double2 x2v = *reinterpret_cast<const double2*>(pt + 2);  // X2, V00
       const double2 v12 = *reinterpret_cast<const double2*>(pt + 4);  // V01, V02
@@ -267,33 +266,54 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
     }
   };
 
-  // One loop, one instance of compute(): refill the queue from the bitmaps until it holds a full
-  // round (or the scan is over), issue that round's gather, compute the round gathered before.
-  uint4 wi = bi[0], wk = bk[0];  // bitmap words are fetched one batch ahead
-  int64_t w0 = 0;                // first word of the next batch
-  uint64_t h0 = 0ull, h1 = 0ull; // hits of the current batch not queued yet
-  int jbase = 0;
-  bool scanning = true;
-  for (;;) {
-    while (scanning && qn < 32) {
-      if (!__any_sync(0xffffffffu, (h0 | h1) != 0ull)) {
-        if (w0 >= Wp) {
-          scanning = false;
-          break;
-        }
-        const uint4 ci = wi, ck = wk;
-        if (w0 + 128 < Wp) {
-          wi = bi[(w0 + 128) >> 2];
-          wk = bk[(w0 + 128) >> 2];
-        }
-        h0 = ((uint64_t)(ci.y & ck.y) << 32) | (ci.x & ck.x);
-        h1 = ((uint64_t)(ci.w & ck.w) << 32) | (ci.z & ck.z);
-        jbase = (int)(w0 + 4 * lane) * 32;
-        w0 += 128;
-        continue;
-      }
+  // Issue the gather of the next round (queue[0, cnt)), move the rest of the queue down, then
+  // compute the previous round.
+  auto round = [&](int cnt) {
+    const uint32_t sa = s_addr + (uint32_t)(rounds & 1) * (32 * kPS * 8);
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const int p = lane + 32 * u;
+      const int row = (p * 171) >> 10;  // p / 6 for p < 192
+      const int piece = p - 6 * row;
+      int j;
+      asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(j) : "r"(q_addr + 4u * row));
+      if (row < cnt) cp_async16(sa + (row * kPS + 2 * piece) * 8, PT + (size_t)j * kPT + 2 * piece);
+    }
+    cp_commit();
+    qn -= cnt;
+    {
+      // queue[32 + x] -> queue[x]
+      int up[3];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) up[u] = sm.queue[32 * (u + 1) + lane];
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 3; ++u) sm.queue[32 * u + lane] = up[u];
+    }
+    if (rounds > 0) {
+      cp_wait<1>();
+      __syncwarp();
+      compute((rounds & 1) ^ 1, cnt_prev);
+    }
+    __syncwarp();
+    cnt_prev = cnt;
+    ++rounds;
+  };
+
+  // bitmap words are fetched one batch ahead
+  uint4 wi = bi[0], wk = bk[0];
+  for (int64_t w0 = 0; w0 < Wp; w0 += 128) {
+    const uint4 ci = wi, ck = wk;
+    if (w0 + 128 < Wp) {
+      wi = bi[(w0 + 128) >> 2];
+      wk = bk[(w0 + 128) >> 2];
+    }
+    uint64_t c0 = ((uint64_t)(ci.y & ck.y) << 32) | (ci.x & ck.x);
+    uint64_t c1 = ((uint64_t)(ci.w & ck.w) << 32) | (ci.z & ck.z);
+    const int jbase = (int)(w0 + 4 * lane) * 32;
+    while (__any_sync(0xffffffffu, (c0 | c1) != 0ull)) {
       // exclusive prefix of the hit counts -> queue slots; hits that do not fit wait for the next pass
-      const int n = __popcll(h0) + __popcll(h1);
+      const int n = __popcll(c0) + __popcll(c1);
       int incl = n;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
@@ -302,53 +322,27 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
       }
       const int total = __shfl_sync(0xffffffffu, incl, 31);
       int pos = qn + incl - n;
-      while (h0 != 0ull && pos < kQueue) {
-        const int b = __ffsll((long long)h0) - 1;
-        h0 &= h0 - 1;
+      while (c0 != 0ull && pos < kQueue) {
+        const int b = __ffsll((long long)c0) - 1;
+        c0 &= c0 - 1;
         sm.queue[pos++] = jbase + b;
       }
-      while (h0 == 0ull && h1 != 0ull && pos < kQueue) {
-        const int b = __ffsll((long long)h1) - 1;
-        h1 &= h1 - 1;
+      while (c0 == 0ull && c1 != 0ull && pos < kQueue) {
+        const int b = __ffsll((long long)c1) - 1;
+        c1 &= c1 - 1;
         sm.queue[pos++] = jbase + 64 + b;
       }
       qn = qn + total < kQueue ? qn + total : kQueue;
       __syncwarp();
+      while (qn >= 32) round(32);
     }
-    const int cnt = qn < 32 ? qn : 32;
-    if (cnt == 0 && cnt_prev == 0) break;
-    if (cnt > 0) {
-      // gather of this round (queue[0, cnt)) into the stage the previous round does not occupy
-      const uint32_t sa = s_addr + (uint32_t)(rounds & 1) * (32 * kPSD * 8);
-#pragma unroll
-      for (int u = 0; u < kPieces; ++u) {
-        const int p = lane + 32 * u;
-        const int row = (p * 205) >> 10;  // p / 5 for p < 160
-        const int piece = p - kPieces * row;
-        int j;
-        asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(j) : "r"(q_addr + 4u * row));
-        if (row < cnt) cp_async16(sa + (row * kPSD + 2 * piece) * 8, PT + (size_t)j * kPT + 2 * piece);
-      }
-      qn -= cnt;
-      int up[3];
-#pragma unroll
-      for (int u = 0; u < 3; ++u) up[u] = sm.queue[32 * (u + 1) + lane];
-      __syncwarp();
-#pragma unroll
-      for (int u = 0; u < 3; ++u) sm.queue[32 * u + lane] = up[u];
-    }
-    cp_commit();  // possibly empty: keeps "all but the newest group" = the previous round's gather
-    if (cnt_prev > 0) {
-      cp_wait<1>();
-      __syncwarp();
-      compute((rounds & 1) ^ 1, cnt_prev);
-    }
-    __syncwarp();
-    cnt_prev = cnt;
-    ++rounds;
   }
-  cp_wait<0>();
-  __syncwarp();
+  if (qn > 0) round(qn);
+  if (rounds > 0) {
+    cp_wait<0>();
+    __syncwarp();
+    compute((rounds - 1) & 1, cnt_prev);
+  }
 
   // leading 8x8 straight from the C fragments; row 8, column 8 and the corner after a fixed-order
   // butterfly over the 32 lanes.  Rows / columns of gauge-pinned parameters (:62-72) are zero.
@@ -707,8 +701,8 @@ int launch_schur_sparse(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
   // BA_PAIRS_REG: the register-accumulator variant below (A/B timing: 40.0 against 38.5 ms at 1000 x 200k)
   static const bool use_reg = std::getenv("BA_PAIRS_REG") != nullptr;
   if (!use_reg) {
-    // 12 warps per SM at 168 registers; BA_PAIRS_OCC15: 15 warps at 128 registers (A/B timing: 39.3 against
-    // 38.5 ms at 1000 x 200k -- the kernel is not occupancy-bound)
+    // 12 warps per SM at 168 registers; BA_PAIRS_OCC15: 128 registers (A/B timing with a 14 KB variant of the
+    // shared-memory layout, 15 warps per SM: 39.3 against 38.5 ms at 1000 x 200k -- not occupancy-bound)
     static const bool occ15 = std::getenv("BA_PAIRS_OCC15") != nullptr;
     auto kern = occ15 ? schur_pairs_kernel<15> : schur_pairs_kernel<12>;
     BA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
