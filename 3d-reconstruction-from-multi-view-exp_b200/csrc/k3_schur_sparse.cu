@@ -36,10 +36,10 @@
 namespace ba {
 
 constexpr int kPS = 14;            // doubles per point row in shared memory (112 B = 7 x 16: odd -> conflict-free LDS.128)
-constexpr int kPieces = 5;         // register variant: 16-byte pieces gathered per point row (the 9 doubles in use)
+constexpr int kPieces = 5;         // 16-byte pieces gathered per point row (the 9 doubles in use)
 constexpr int kPairTile = 32;      // pairs are scheduled in kPairTile x kPairTile tiles of (i, k)
 constexpr int kDiagPart = 54;      // 45 unique entries of the diagonal block + 9 rhs entries
-constexpr int kQueue = 128;        // queue capacity (point ids)
+constexpr int kQueue = 128;        // queue capacity (point ids); a power of two: the queue is a ring
 constexpr int kFragX = 32 * 8 + 4; // doubles between the two rows of a fragment array (+4: conflict-free fragment loads)
 
 // ---- index: per camera bitmap over points -------------------------------------------------------
@@ -165,6 +165,7 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
   const int frag_base = (fkq & 1) * kFragX + (fkq >> 1) * 8;
 
   int qn = 0;           // entries queued
+  int head = 0;         // ring position of the first queued entry
   int rounds = 0;       // rounds whose gather has been issued
   int cnt_prev = 0;     // valid lanes of the round waiting in stage (rounds - 1) & 1
 
@@ -195,7 +196,7 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
         const double mk12 = v02 * sk.bX[0] + v12_ * sk.bX[1] + v22 * sk.bX[2];
         const double rr = si.r * sk.r;
         const double rr2 = rr * rr;
-        const double sc = 4.0 / (rr2 * rr2);
+        const double sc = 4.0 * rcp_nr(rr2 * rr2);
         const double g00 = sc * (si.aX[0] * mk00 + si.aX[1] * mk01 + si.aX[2] * mk02);
         const double g01 = sc * (si.aX[0] * mk10 + si.aX[1] * mk11 + si.aX[2] * mk12);
         const double g10 = sc * (si.bX[0] * mk00 + si.bX[1] * mk01 + si.bX[2] * mk02);
@@ -266,30 +267,22 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
     }
   };
 
-  // Issue the gather of the next round (queue[0, cnt)), move the rest of the queue down, then
-  // compute the previous round.
+  // Issue the gather of the next round (the first cnt entries of the ring), then compute the previous
+  // round.
   auto round = [&](int cnt) {
     const uint32_t sa = s_addr + (uint32_t)(rounds & 1) * (32 * kPS * 8);
 #pragma unroll
-    for (int u = 0; u < 6; ++u) {
+    for (int u = 0; u < kPieces; ++u) {  // X (3) + V^-1 (6) = 72 B: the first five 16-byte pieces of the row
       const int p = lane + 32 * u;
-      const int row = (p * 171) >> 10;  // p / 6 for p < 192
-      const int piece = p - 6 * row;
+      const int row = (p * 205) >> 10;  // p / 5 for p < 160
+      const int piece = p - kPieces * row;
       int j;
-      asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(j) : "r"(q_addr + 4u * row));
+      asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(j) : "r"(q_addr + 4u * (uint32_t)((head + row) & (kQueue - 1))));
       if (row < cnt) cp_async16(sa + (row * kPS + 2 * piece) * 8, PT + (size_t)j * kPT + 2 * piece);
     }
     cp_commit();
     qn -= cnt;
-    {
-      // queue[32 + x] -> queue[x]
-      int up[3];
-#pragma unroll
-      for (int u = 0; u < 3; ++u) up[u] = sm.queue[32 * (u + 1) + lane];
-      __syncwarp();
-#pragma unroll
-      for (int u = 0; u < 3; ++u) sm.queue[32 * u + lane] = up[u];
-    }
+    head = (head + cnt) & (kQueue - 1);  // the queue is a ring: nothing moves
     if (rounds > 0) {
       cp_wait<1>();
       __syncwarp();
@@ -325,12 +318,12 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
       while (c0 != 0ull && pos < kQueue) {
         const int b = __ffsll((long long)c0) - 1;
         c0 &= c0 - 1;
-        sm.queue[pos++] = jbase + b;
+        sm.queue[(head + pos++) & (kQueue - 1)] = jbase + b;
       }
       while (c0 == 0ull && c1 != 0ull && pos < kQueue) {
         const int b = __ffsll((long long)c1) - 1;
         c1 &= c1 - 1;
-        sm.queue[pos++] = jbase + 64 + b;
+        sm.queue[(head + pos++) & (kQueue - 1)] = jbase + 64 + b;
       }
       qn = qn + total < kQueue ? qn + total : kQueue;
       __syncwarp();
