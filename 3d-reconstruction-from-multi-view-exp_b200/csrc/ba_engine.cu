@@ -2,6 +2,7 @@
 // ingestion (camera-major index built on the device), phase sequencing of the LM loop.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -85,7 +86,7 @@ static inline int64_t round_up64(int64_t v, int64_t m) { return (v + m - 1) / m 
 // (kept for the life of the process) and sending them on its own stream while it copies the next;
 // the caller's stream waits for all of them.  Pinned or small sources take the plain path.
 constexpr int kUpThreads = 8, kUpBufs = 2;
-constexpr size_t kUpChunk = (size_t)1 << 20, kUpMin = (size_t)32 << 20;  // 16 MB pinned in all (page-locking costs ~3 ms per MB, once per process)
+constexpr size_t kUpChunk = (size_t)1 << 20, kUpMin = (size_t)64 << 20;  // 16 MB pinned in all (page-locking costs ~3 ms per MB, once per process)
 struct UploadPool {
   int device = -1;
   void* buf[kUpThreads][kUpBufs] = {};
@@ -129,15 +130,24 @@ static bool staged_upload(void* dst, const void* src, size_t bytes, cudaStream_t
   if (cudaEventRecord(g_up.start, s) != cudaSuccess) return false;
   const size_t n_chunks = (bytes + kUpChunk - 1) / kUpChunk;
   bool failed[kUpThreads] = {};
+  // the ranks of a multi-GPU job on one node share the host cores (torchrun exports LOCAL_WORLD_SIZE)
+  int n_threads = kUpThreads;
+  {
+    const char* lws = std::getenv("LOCAL_WORLD_SIZE");
+    const int ranks = lws ? std::max(1, std::atoi(lws)) : 1;
+    const int cores = (int)std::thread::hardware_concurrency();
+    if (cores > 0) n_threads = std::min(kUpThreads, std::max(1, cores / (2 * ranks)));
+  }
+  if (n_threads < 2) return false;
   std::vector<std::thread> workers;
-  for (int t = 0; t < kUpThreads; ++t)
+  for (int t = 0; t < n_threads; ++t)
     workers.emplace_back([&, t]() {
       if (cudaSetDevice(device) != cudaSuccess || cudaStreamWaitEvent(g_up.st[t], g_up.start, 0) != cudaSuccess) {
         failed[t] = true;
         return;
       }
       int round = 0;
-      for (size_t c = (size_t)t; c < n_chunks; c += kUpThreads, ++round) {
+      for (size_t c = (size_t)t; c < n_chunks; c += (size_t)n_threads, ++round) {
         const int b = round % kUpBufs;
         const size_t off_b = c * kUpChunk, len = bytes - off_b < kUpChunk ? bytes - off_b : kUpChunk;
         if (round >= kUpBufs && cudaEventSynchronize(g_up.ev[t][b]) != cudaSuccess) { failed[t] = true; return; }
@@ -152,7 +162,7 @@ static bool staged_upload(void* dst, const void* src, size_t bytes, cudaStream_t
     });
   for (auto& w : workers) w.join();
   bool ok = true;
-  for (int t = 0; t < kUpThreads; ++t) {
+  for (int t = 0; t < n_threads; ++t) {
     // the staging buffers are reused by the next call: their transfers must have left them
     if (failed[t] || cudaStreamWaitEvent(s, g_up.done[t], 0) != cudaSuccess || cudaEventSynchronize(g_up.done[t]) != cudaSuccess)
       ok = false;
