@@ -676,7 +676,8 @@ static bool plan_for_tma() {
 // diagonal.  A warp sits on scheduler partition (warp % 4) with its own FP64 pipe: a CTA that has
 // an SM to itself takes as long as its busiest partition; with several CTAs per SM the partitions
 // even out and the mean counts.
-static double tile_weight(int TILE, int WR, int WC, int occ, int ti, int tj, int n_valid, int64_t k_pad = 0) {
+static double tile_weight(int TILE, int WR, int WC, int occ, int ti, int tj, int n_valid, int64_t k_pad = 0,
+                          double floor_override = -1.0) {
   const int WM = TILE / WR, WN = TILE / WC, FM = WM / 8, FN = WN / 8;
   double load[4] = {0, 0, 0, 0};
   const bool tma_tile = TILE == kTmaTile && occ == 1 && plan_for_tma();
@@ -726,6 +727,7 @@ static double tile_weight(int TILE, int WR, int WC, int occ, int ti, int tj, int
   const bool small_operand = k_pad > 0 && (double)k_pad * n_valid * 8.0 <= 256.0 * 1024 * 1024;
   double floor_w = occ == 1 ? (plan_for_tma() ? (small_operand ? 1.0 : 0.5) : 0.75) : 1.0;
   if (const char* f = std::getenv("BA_SYRK_FLOOR")) floor_w = std::atof(f);  // tuning experiments only
+  if (floor_override >= 0.0) floor_w = floor_override;
   return w > floor_w ? w : floor_w;
 }
 
@@ -762,15 +764,21 @@ static SyrkPlan plan_syrk(int n_pad, int TILE, int WR, int WC, int64_t k_pad, in
   const int n_tiles = nt1 * (nt1 + 1) / 2;
   const int64_t n_chunks = k_pad / KC;
   const int slots = num_sms * occ;
-  std::vector<double> w(n_tiles);
+  std::vector<double> w(n_tiles), w_run(n_tiles);  // w: decides the cuts; w_run: the modelled duration per k-row
+  static const char* lpt_env = std::getenv("BA_SYRK_LPT");  // "0" / "1": A/B timing
+  const bool lpt = lpt_env ? std::atoi(lpt_env) != 0 : (double)k_pad * n_pad * 8.0 <= 116.0 * 1024 * 1024;
+  static const double run_floor = std::getenv("BA_SYRK_RUN_FLOOR") ? std::atof(std::getenv("BA_SYRK_RUN_FLOOR")) : 0.5;
   const int tall_row = tall_tile_row(n_pad, TILE, occ);
   // absorbed[t]: thin tile (nt1 - 1, tj), tj < tall_row: computed by the tall tile (tall_row, tj)
   std::vector<char> absorbed(n_tiles, 0), is_tall(n_tiles, 0);
   for (int t = 0, ti = 0; ti < nt1; ++ti)
     for (int tj = 0; tj <= ti; ++tj, ++t) {
       w[t] = tile_weight(TILE, WR, WC, occ, ti, tj, n_pad, k_pad);
+      // longest-first schedules are simulated with what a tile really costs (its fragments, down to
+      // the rate of the TMA ring), not with the weight that decides the cuts
+      w_run[t] = lpt ? tile_weight(TILE, WR, WC, occ, ti, tj, n_pad, k_pad, run_floor) : w[t];
       if (tall_row >= 0 && tj < tall_row) {
-        if (ti == tall_row) { is_tall[t] = 1; w[t] *= 1.0 + 2.0 / 16.0; }  // two more fragments per warp
+        if (ti == tall_row) { is_tall[t] = 1; w[t] *= 1.0 + 2.0 / 16.0; w_run[t] *= 1.0 + 2.0 / 16.0; }  // two more fragments per warp
         if (ti == nt1 - 1) absorbed[t] = 1;
       }
     }
@@ -783,7 +791,7 @@ static SyrkPlan plan_syrk(int n_pad, int TILE, int WR, int WC, int64_t k_pad, in
   const double overhead = 48.0;  // k-rows of a full tile: pipeline fill + partial-tile write
 
   auto build = [&](int64_t S, SyrkPlan* out) -> double {
-    struct Piece { int t; int64_t lo, hi; };
+    struct Piece { int t; int64_t lo, hi; int kidx; };  // kidx: position among its tile's pieces (ascending k)
     std::vector<Piece> pieces;
     std::vector<int> count(n_tiles);
     for (int t = 0; t < n_tiles; ++t) {
@@ -793,11 +801,18 @@ static SyrkPlan plan_syrk(int n_pad, int TILE, int WR, int WC, int64_t k_pad, in
       const int64_t cps = (n_chunks + p - 1) / p;
       p = (n_chunks + cps - 1) / cps;
       count[t] = (int)p;
-      for (int64_t k = 0; k < p; ++k) pieces.push_back({t, k * cps, std::min<int64_t>(n_chunks, (k + 1) * cps)});
+      for (int64_t k = 0; k < p; ++k) pieces.push_back({t, k * cps, std::min<int64_t>(n_chunks, (k + 1) * cps), (int)k});
     }
     std::stable_sort(pieces.begin(), pieces.end(), [](const Piece& a, const Piece& b) {
       return a.lo != b.lo ? a.lo < b.lo : a.t < b.t;
     });
+    // An operand that stays in the L2 whatever the order (C2: 110 MB) is scheduled longest item first:
+    // with ~2 waves of items of unequal duration (full tiles 1.0, diagonal / ragged ones ~0.55 per
+    // k-row) the k-major order leaves SMs with two long items next to SMs with two short ones.
+    if (lpt)
+      std::stable_sort(pieces.begin(), pieces.end(), [&](const Piece& a, const Piece& b) {
+        return w_run[a.t] * (double)(a.hi - a.lo) > w_run[b.t] * (double)(b.hi - b.lo);
+      });
     // list scheduling on `slots` slots, each running at 1/occ of an SM
     std::priority_queue<double, std::vector<double>, std::greater<double>> free_at;
     for (int k = 0; k < slots; ++k) free_at.push(0.0);
@@ -805,7 +820,7 @@ static SyrkPlan plan_syrk(int n_pad, int TILE, int WR, int WC, int64_t k_pad, in
     for (const Piece& pc : pieces) {
       const double start = free_at.top();
       free_at.pop();
-      const double end = start + (w[pc.t] * (double)(pc.hi - pc.lo) * KC + overhead) * occ;
+      const double end = start + (w_run[pc.t] * (double)(pc.hi - pc.lo) * KC + overhead) * occ;
       free_at.push(end);
       makespan = std::max(makespan, end);
     }
@@ -820,16 +835,15 @@ static SyrkPlan plan_syrk(int n_pad, int TILE, int WR, int WC, int64_t k_pad, in
       for (int t = 0; t < n_tiles; ++t)
         out->tile_first[t + 1] = out->tile_first[t] + (absorbed[t] ? count[tile_index(tall_row, tj_of[t])] : count[t]);
       out->tile_items.assign(out->tile_first[n_tiles], 0);
-      std::vector<int> fill(n_tiles, 0);
       int n_slots = (int)pieces.size();  // slot of an item = its index; the second slots follow
-      for (const Piece& pc : pieces) {  // sorted by lo: per tile the pieces arrive in ascending k order
+      for (const Piece& pc : pieces) {  // launch order; a tile's partial tiles are listed in ascending k order
         const int item = (int)out->items.size();
-        out->tile_items[out->tile_first[pc.t] + fill[pc.t]++] = item;
+        out->tile_items[out->tile_first[pc.t] + pc.kidx] = item;
         int slot2 = -1;
         if (is_tall[pc.t]) {
           slot2 = n_slots++;
           const int thin = tile_index(nt1 - 1, tj_of[pc.t]);
-          out->tile_items[out->tile_first[thin] + fill[thin]++] = slot2;
+          out->tile_items[out->tile_first[thin] + pc.kidx] = slot2;
         }
         out->items.push_back({ti_of[pc.t], tj_of[pc.t], (int)pc.lo, (int)pc.hi, slot2});
       }
