@@ -343,9 +343,10 @@ __device__ __forceinline__ void scaled_point_rows(const double* ax, const double
 __device__ __forceinline__ double y_entry(double ja, double jb, double ta, double tb) {
   return fma(ja, ta, __dmul_rn(jb, tb));
 }
-// acc += x0 y0 + x1 y1, pinned: the block sums of K2a / the camera blocks, stored rows or re-derived
+// acc += x0 y0 + x1 y1 as two chained FMAs, pinned: the block sums of K2a / the camera blocks, stored
+// rows or re-derived
 __device__ __forceinline__ double pair_accumulate(double acc, double x0, double y0, double x1, double y1) {
-  return __dadd_rn(acc, fma(x1, y1, __dmul_rn(x0, y0)));
+  return fma(x1, y1, fma(x0, y0, acc));
 }
 #endif
 

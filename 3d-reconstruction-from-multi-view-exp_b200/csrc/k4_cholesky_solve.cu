@@ -106,9 +106,9 @@ __global__ void camera_update_kernel(int M, double f0, const double* __restrict_
 }
 
 // ---- point back-substitution + trial cost (:152, :155, :159-162) -------------------------------
-// MF (dense scenes, see dense_matrix_free): Y is not read back (216 B per observation) but re-derived
-// from the camera table of the linearisation state, X_j and L_j^-1 with the arithmetic K2b wrote it
-// with (obs_jacobian, scaled_point_rows, y_entry: the same bits, so the step is the same step);
+// MF (dense scenes, see dense_matrix_free): Y is not read back (216 B per observation); its product
+// with the camera step is re-derived from the camera table of the linearisation state, X_j and L_j^-1
+// (obs_jacobian, scaled_point_rows: the rows K2b formed Y from);
 // both camera tables and the camera step sit in shared memory.
 template <bool DENSE, bool MF>
 __global__ void __launch_bounds__(256)
@@ -154,16 +154,20 @@ point_update_cost_kernel(int64_t N, int M, const int64_t* __restrict__ obs_ptr,
         obs_jacobian(s_tab0 + (size_t)i * kTabStride, xj0, xj1, xj2, J);
         double ta[3], tb[3];
         scaled_point_rows(J.ax, J.bx, m00, m10, m11, m20, m21, m22, ta, tb);
+        // sum_a Y[a][d] dxi[a] = ta[d] (Jc row a . dxi) + tb[d] (Jc row b . dxi): 24 FMAs instead of
+        // forming the 27 entries of Y (the step agrees with the stored-Y path to rounding, not bitwise)
         const double* d = s_dxi + 9 * i;
+        double ua = 0.0, ub = 0.0;
 #pragma unroll
         for (int a = 0; a < 9; ++a) {
           const bool pin = (mask >> a) & 1u;
-          const double ja = pin ? 0.0 : J.ja[a], jb = pin ? 0.0 : J.jb[a];
-          const double da = d[a];
-          s0 = fma(y_entry(ja, jb, ta[0], tb[0]), da, s0);
-          s1 = fma(y_entry(ja, jb, ta[1], tb[1]), da, s1);
-          s2 = fma(y_entry(ja, jb, ta[2], tb[2]), da, s2);
+          const double da = pin ? 0.0 : d[a];
+          ua = fma(J.ja[a], da, ua);
+          ub = fma(J.jb[a], da, ub);
         }
+        s0 = fma(ta[0], ua, fma(tb[0], ub, s0));
+        s1 = fma(ta[1], ua, fma(tb[1], ub, s1));
+        s2 = fma(ta[2], ua, fma(tb[2], ub, s2));
       }
     } else {
     for (int64_t o = lo + lane; o < hi; o += 32) {
