@@ -808,8 +808,18 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
     constexpr size_t kStepSmem = (2 * NB * (NB + 1) + 5 * NB + 2 * NB * kSLD) * sizeof(double);
     BA_CUDA(cudaFuncSetAttribute(chol_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStepSmem));
     static const bool no_persist = std::getenv("BA_CHOL_NO_PERSIST") != nullptr;  // A/B timing: one launch per panel
-    if (!no_persist) {
+    // the persistent kernel needs its CTAs co-resident (cooperative launch): ask once how many fit
+    static int fused_ctas_per_sm = -1;
+    if (fused_ctas_per_sm < 0) {
       BA_CUDA(cudaFuncSetAttribute(chol_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStepSmem));
+      int per_sm = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_fused_kernel, kPanelThreads, kStepSmem) != cudaSuccess) {
+        cudaGetLastError();
+        per_sm = 0;
+      }
+      fused_ctas_per_sm = per_sm;
+    }
+    if (!no_persist && fused_ctas_per_sm > 0) {
       // grid: enough CTAs for the busiest step (panel blocks + the tiles of the previous panel's update)
       int want = 1;
       {
@@ -826,7 +836,8 @@ int launch_cholesky_solve(ba_engine* e, bool conditional, cudaStream_t s) {
           if (blocks > want) want = blocks;
         }
       }
-      const int G = want < e->num_sms ? want : e->num_sms;
+      const int fit = e->num_sms * fused_ctas_per_sm;
+      const int G = want < fit ? want : fit;
       BA_CUDA(cudaMemsetAsync(e->chol_bar, 0, sizeof(unsigned int), s));
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(G);
