@@ -140,6 +140,12 @@ struct ba_engine {
   double* Yt = nullptr;   // dense: [k_pad][n_pad]
   double* Ysp = nullptr;  // sparse: [nobs][27]
   double* PT = nullptr;   // sparse: [N][kPT] point table of the pair kernel (X, damped V^-1)
+  // sparse: the common points of every camera pair, compacted once per engine (visibility does not
+  // change between iterations): pair_ptr [n_pair_items + 1], pair_pts [pair_total] ascending point ids;
+  // null when the lists would not fit the memory budget (the pair kernel then scans the bitmaps)
+  int64_t* pair_ptr = nullptr;
+  int32_t* pair_pts = nullptr;
+  int64_t pair_total = 0;
   double* red = nullptr;  // [n_pad*n_pad | M*81 | M*9]
   int64_t red_len = 0;
   bool red_in_window = false;  // red lives in the exchange window (freed with it)

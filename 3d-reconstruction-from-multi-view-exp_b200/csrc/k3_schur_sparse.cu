@@ -29,6 +29,8 @@
 //
 // schur_diag_kernel: the diagonal blocks P[9i..][9i..] and the rhs row, a segmented reduction over
 // the camera's observations in camera-major order (fixed chunking and order).
+#include <cub/device/device_scan.cuh>
+
 #include <cstdlib>
 
 #include "ba_common.cuh"
@@ -52,10 +54,115 @@ __global__ void bitmap_fill_kernel(int64_t nobs, int64_t Wp, const int32_t* __re
   }
 }
 
+// ---- static pair lists ----------------------------------------------------------------------------
+// Which points two cameras share does not change between iterations, but intersecting the bitmaps,
+// compacting the hits and queueing them was 55-60 % of the pair kernel's time (stall samples, DESIGN.md
+// section 3b) -- every solve.  The intersection is therefore done ONCE per engine: pair_count_kernel
+// counts the common points of every pair item, an exclusive sum gives the offsets, pair_fill_kernel
+// writes the ascending point ids.  4 B per pair-point (C4: 19.8 GB of the 180 GB); if that exceeds a
+// third of the free memory the lists are not built and the pair kernel scans the bitmaps as before.
+__device__ __forceinline__ bool pair_from_linear(int64_t t, int M, int& i, int& k);
+
+__global__ void __launch_bounds__(256)
+pair_count_kernel(int M, int64_t Wp, int64_t n_items, const uint32_t* __restrict__ bits, int64_t* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (t > n_items) return;
+  int i, k;
+  int64_t acc = 0;
+  if (t < n_items && pair_from_linear(t, M, i, k)) {
+    const uint4* bi = reinterpret_cast<const uint4*>(bits + (size_t)i * Wp);
+    const uint4* bk = reinterpret_cast<const uint4*>(bits + (size_t)k * Wp);
+    for (int64_t w = lane; w < Wp / 4; w += 32) {
+      const uint4 a = bi[w], b = bk[w];
+      acc += __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) counts[t] = acc;  // counts[n_items] = 0: the exclusive sum then ends with the total
+}
+
+__global__ void __launch_bounds__(256)
+pair_fill_kernel(int M, int64_t Wp, int64_t n_items, const uint32_t* __restrict__ bits,
+                 const int64_t* __restrict__ ptr, int32_t* __restrict__ pts) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  int i, k;
+  if (t >= n_items || !pair_from_linear(t, M, i, k)) return;
+  const uint4* bi = reinterpret_cast<const uint4*>(bits + (size_t)i * Wp) + lane;
+  const uint4* bk = reinterpret_cast<const uint4*>(bits + (size_t)k * Wp) + lane;
+  int64_t running = ptr[t];
+  for (int64_t w0 = 0; w0 < Wp; w0 += 128) {  // 4096 points per batch, 128 per lane: ascending over the lanes
+    const uint4 a = bi[w0 >> 2], b = bk[w0 >> 2];
+    uint64_t c0 = ((uint64_t)(a.y & b.y) << 32) | (a.x & b.x);
+    uint64_t c1 = ((uint64_t)(a.w & b.w) << 32) | (a.z & b.z);
+    const int n = __popcll(c0) + __popcll(c1);
+    int incl = n;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int32_t* dst = pts + running + (incl - n);
+    const int jbase = (int)(w0 + 4 * lane) * 32;
+    while (c0 != 0ull) {
+      *dst++ = jbase + __ffsll((long long)c0) - 1;
+      c0 &= c0 - 1;
+    }
+    while (c1 != 0ull) {
+      *dst++ = jbase + 64 + __ffsll((long long)c1) - 1;
+      c1 &= c1 - 1;
+    }
+    running += total;
+  }
+}
+
 int build_pair_index(ba_engine* e, cudaStream_t s) {
   BA_CUDA(cudaMemsetAsync(e->bits, 0, (size_t)e->M * e->Wp * sizeof(uint32_t), s));
   BA_CUDA(cudaMemsetAsync(e->PT, 0, (size_t)e->N * kPT * sizeof(double), s));
   bitmap_fill_kernel<<<e->num_sms * 8, 256, 0, s>>>(e->nobs, e->Wp, e->obs_cam, e->obs_pt, e->bits);
+  BA_LAUNCH_CHECK();
+  static const bool no_lists = std::getenv("BA_PAIRS_NO_LIST") != nullptr;  // A/B timing: scan the bitmaps every solve
+  if (no_lists) return BA_OK;
+  const int nt = (e->M + kPairTile - 1) / kPairTile;
+  const int64_t n_items = (int64_t)nt * (nt + 1) / 2 * kPairTile * kPairTile;
+  if (n_items >= ((int64_t)1 << 31)) return BA_OK;
+  if (cudaMallocAsync(reinterpret_cast<void**>(&e->pair_ptr), (size_t)(n_items + 1) * sizeof(int64_t), (cudaStream_t)0) != cudaSuccess) {
+    cudaGetLastError();
+    e->pair_ptr = nullptr;
+    return BA_OK;
+  }
+  BA_CUDA(cudaStreamSynchronize((cudaStream_t)0));  // the allocation is ordered on the default stream
+  const unsigned blocks = (unsigned)((n_items + 1 + 7) / 8);
+  pair_count_kernel<<<blocks, 256, 0, s>>>(e->M, e->Wp, n_items, e->bits, e->pair_ptr);
+  BA_LAUNCH_CHECK();
+  {
+    size_t tmp_bytes = 0;
+    BA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, e->pair_ptr, e->pair_ptr, (int)(n_items + 1), s));
+    void* tmp = nullptr;
+    BA_CUDA(cudaMallocAsync(&tmp, tmp_bytes, s));
+    BA_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, e->pair_ptr, e->pair_ptr, (int)(n_items + 1), s));
+    BA_CUDA(cudaFreeAsync(tmp, s));
+  }
+  int64_t total = 0;
+  BA_CUDA(cudaMemcpyAsync(&total, e->pair_ptr + n_items, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  BA_CUDA(cudaStreamSynchronize(s));
+  size_t free_b = 0, total_b = 0;
+  BA_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t need = (size_t)(total > 0 ? total : 1) * sizeof(int32_t);
+  if (need > free_b / 3 ||
+      cudaMallocAsync(reinterpret_cast<void**>(&e->pair_pts), need, (cudaStream_t)0) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFreeAsync(e->pair_ptr, (cudaStream_t)0);
+    e->pair_ptr = nullptr;
+    e->pair_pts = nullptr;
+    return BA_OK;
+  }
+  BA_CUDA(cudaStreamSynchronize((cudaStream_t)0));
+  e->pair_total = total;
+  pair_fill_kernel<<<(unsigned)((n_items + 7) / 8), 256, 0, s>>>(e->M, e->Wp, n_items, e->bits, e->pair_ptr, e->pair_pts);
   BA_LAUNCH_CHECK();
   return BA_OK;
 }
@@ -127,11 +234,14 @@ __device__ __forceinline__ SideJac side_jacobian(const double* __restrict__ c, d
   return s;
 }
 
-template <int MINB>
+// LIST: the pair's common points come from the static lists (build_pair_index) -- one coalesced load of
+// 32 ids per round, fetched a round ahead -- instead of the bitmap scan with its queue.
+template <int MINB, bool LIST>
 __global__ void __launch_bounds__(32, MINB)
 schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bits,
                    const double* __restrict__ camtab, double f0, const double* __restrict__ PT,
-                   double* __restrict__ P, int ld, const ba_lm_state* ctl) {
+                   double* __restrict__ P, int ld, const ba_lm_state* ctl,
+                   const int64_t* __restrict__ pair_ptr, const int32_t* __restrict__ pair_pts) {
   if (ctl && ctl->done) return;
   int i, k;
   if (!pair_from_linear(blockIdx.x, M, i, k)) return;
@@ -293,6 +403,34 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
     ++rounds;
   };
 
+  if (LIST) {
+    const int64_t lo = pair_ptr[blockIdx.x], hi = pair_ptr[blockIdx.x + 1];
+    int jnext = lo + lane < hi ? pair_pts[lo + lane] : -1;  // the ids of the first round
+    for (int64_t base = lo; base < hi; base += 32) {
+      const int cnt = hi - base < 32 ? (int)(hi - base) : 32;
+      const int jcur = jnext;
+      if (base + 32 < hi) jnext = base + 32 + lane < hi ? pair_pts[base + 32 + lane] : -1;
+      // gather of this round: five consecutive lanes per row
+      const uint32_t sa = s_addr + (uint32_t)(rounds & 1) * (32 * kPS * 8);
+#pragma unroll
+      for (int u = 0; u < kPieces; ++u) {
+        const int p = lane + 32 * u;
+        const int row = (p * 205) >> 10;  // p / 5 for p < 160
+        const int piece = p - kPieces * row;
+        const int jr = __shfl_sync(0xffffffffu, jcur, row);
+        if (row < cnt) cp_async16(sa + (row * kPS + 2 * piece) * 8, PT + (size_t)jr * kPT + 2 * piece);
+      }
+      cp_commit();
+      if (rounds > 0) {
+        cp_wait<1>();
+        __syncwarp();
+        compute((rounds & 1) ^ 1, cnt_prev);
+      }
+      __syncwarp();
+      cnt_prev = cnt;
+      ++rounds;
+    }
+  } else {
   // bitmap words are fetched one batch ahead
   uint4 wi = bi[0], wk = bk[0];
   for (int64_t w0 = 0; w0 < Wp; w0 += 128) {
@@ -331,6 +469,7 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
     }
   }
   if (qn > 0) round(qn);
+  }
   if (rounds > 0) {
     cp_wait<0>();
     __syncwarp();
@@ -368,7 +507,7 @@ schur_pairs_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bit
   }
 }
 
-// ---- register-accumulator variant -----------------------------------------------------------------
+// ---- register-accumulator variant (the default when the static pair lists exist) -------------------
 // What ncu said about the kernel above (profiles/r2_pairs_*): DMMA shares the FP64 datapath with DFMA
 // (fp64_peak mode 2: 32 TF/s in sum), so the tensor instructions buy no arithmetic, and building
 // their fragments costs 128 shared-memory wavefronts per 32 pair-points; and, by stall samples, 60 %
@@ -396,10 +535,12 @@ struct PairRegSmem {
 };
 static_assert(27 * 33 <= 2 * 32 * kPS, "reduction scratch must fit the staging buffers");
 
+template <bool LIST>
 __global__ void __launch_bounds__(32, 8)
 schur_pairs_reg_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__ bits,
                        const double* __restrict__ camtab, double f0, const double* __restrict__ PT,
-                       double* __restrict__ P, int ld, const ba_lm_state* ctl) {
+                       double* __restrict__ P, int ld, const ba_lm_state* ctl,
+                       const int64_t* __restrict__ pair_ptr, const int32_t* __restrict__ pair_pts) {
   if (ctl && ctl->done) return;
   int i, k;
   if (!pair_from_linear(blockIdx.x, M, i, k)) return;
@@ -491,6 +632,41 @@ schur_pairs_reg_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__
     }
   };
 
+  if (LIST) {
+    // static pair lists (build_pair_index): 32 ids per round with one coalesced load, a round ahead
+    const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(sm.stage[0]);
+    const int64_t lo = pair_ptr[blockIdx.x], hi = pair_ptr[blockIdx.x + 1];
+    int jnext = lo + lane < hi ? pair_pts[lo + lane] : -1;
+    int rounds = 0, cnt_prev = 0;
+    for (int64_t base = lo; base < hi; base += 32) {
+      const int cnt = hi - base < 32 ? (int)(hi - base) : 32;
+      const int jcur = jnext;
+      if (base + 32 < hi) jnext = base + 32 + lane < hi ? pair_pts[base + 32 + lane] : -1;
+      const uint32_t dst = stage0 + (uint32_t)(rounds & 1) * (32 * kPS * 8);
+#pragma unroll
+      for (int u = 0; u < kPieces; ++u) {
+        const int p = lane + 32 * u;
+        const int row = (p * 205) >> 10;  // p / 5 for p < 160
+        const int piece = p - kPieces * row;
+        const int jr = __shfl_sync(0xffffffffu, jcur, row);
+        if (row < cnt) cp_async16(dst + (uint32_t)(row * kPS + 2 * piece) * 8u, PT + (size_t)jr * kPT + 2 * piece);
+      }
+      cp_commit();
+      if (rounds > 0) {
+        cp_wait<1>();
+        __syncwarp();
+        if (lane < cnt_prev) compute((rounds & 1) ^ 1);
+      }
+      __syncwarp();
+      cnt_prev = cnt;
+      ++rounds;
+    }
+    if (rounds > 0) {
+      cp_wait<0>();
+      __syncwarp();
+      if (lane < cnt_prev) compute((rounds - 1) & 1);
+    }
+  } else {
   // ---- the lanes' walk over the groups -----------------------------------------------------------
   // Groups are CLAIMED, not owned: a lane that has moved its waiting group into its registers takes
   // the next unclaimed group (ballot + popc, warp-uniform counter) and starts its prefetch.  Every
@@ -576,6 +752,7 @@ schur_pairs_reg_kernel(int M, int axis, int64_t Wp, const uint32_t* __restrict__
     if (prev) compute((r & 1) ^ 1);
     prev = hit;
     if (!__any_sync(0xffffffffu, hit || slot_g >= 0)) break;  // `hit` lanes still owe one compute
+  }
   }
   __syncwarp();
 
@@ -691,22 +868,29 @@ int launch_schur_sparse(ba_engine* e, const ba_lm_state* ctl, cudaStream_t s) {
     set_error("too many camera pairs for one launch (M=%d)", e->M);
     return BA_ERR_INVALID;
   }
-  // BA_PAIRS_REG: the register-accumulator variant below (A/B timing: 40.0 against 38.5 ms at 1000 x 200k)
-  static const bool use_reg = std::getenv("BA_PAIRS_REG") != nullptr;
+  // Variant: with the static pair lists the register-accumulator kernel is the faster one (27.0 against
+  // 27.8 ms at 1000 x 200k), with the bitmap scan the DMMA kernel (35.9 against 40.0).  BA_PAIRS_REG /
+  // BA_PAIRS_DMMA force one of them (A/B timing).
+  static const bool force_reg = std::getenv("BA_PAIRS_REG") != nullptr;
+  static const bool force_dmma = std::getenv("BA_PAIRS_DMMA") != nullptr;
+  const bool have_lists = e->pair_ptr != nullptr && e->pair_pts != nullptr;
+  const bool use_reg = force_reg || (have_lists && !force_dmma);
   if (!use_reg) {
     // 12 warps per SM at 168 registers; BA_PAIRS_OCC15: 128 registers (A/B timing with a 14 KB variant of the
     // shared-memory layout, 15 warps per SM: 39.3 against 38.5 ms at 1000 x 200k -- not occupancy-bound)
     static const bool occ15 = std::getenv("BA_PAIRS_OCC15") != nullptr;
-    auto kern = occ15 ? schur_pairs_kernel<15> : schur_pairs_kernel<12>;
+    const bool lists = e->pair_ptr != nullptr && e->pair_pts != nullptr;
+    auto kern = lists ? schur_pairs_kernel<12, true> : occ15 ? schur_pairs_kernel<15, false> : schur_pairs_kernel<12, false>;
     BA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  (int)cudaSharedmemCarveoutMaxShared));
     kern<<<(unsigned)n_items, 32, 0, s>>>(e->M, e->axis, e->Wp, e->bits, e->camtab[0], e->f0, e->PT, e->P(),
-                                         e->n_pad, ctl);
+                                         e->n_pad, ctl, e->pair_ptr, e->pair_pts);
   } else {
-    BA_CUDA(cudaFuncSetAttribute(schur_pairs_reg_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 (int)cudaSharedmemCarveoutMaxShared));
-    schur_pairs_reg_kernel<<<(unsigned)n_items, 32, 0, s>>>(e->M, e->axis, e->Wp, e->bits, e->camtab[0], e->f0,
-                                                           e->PT, e->P(), e->n_pad, ctl);
+    const bool lists = e->pair_ptr != nullptr && e->pair_pts != nullptr;
+    auto kern = lists ? schur_pairs_reg_kernel<true> : schur_pairs_reg_kernel<false>;
+    BA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    kern<<<(unsigned)n_items, 32, 0, s>>>(e->M, e->axis, e->Wp, e->bits, e->camtab[0], e->f0, e->PT, e->P(), e->n_pad, ctl,
+                                         e->pair_ptr, e->pair_pts);
   }
   BA_LAUNCH_CHECK();
   return BA_OK;
