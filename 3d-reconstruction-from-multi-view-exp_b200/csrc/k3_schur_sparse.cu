@@ -16,16 +16,30 @@
 // operations and 96 B of L2 traffic per pair-point instead of 2 x 216 B of gathered Y blocks,
 // which at C4 (19 GB of blocks, each read m_j = 100 times) made the kernel latency/HBM bound.
 //
-// schur_pairs_kernel: ONE WARP PER CAMERA PAIR (i, k), k < i.  The warp intersects the two cameras'
-// point bitmaps 4096 points at a time (128 bits per lane); hits (point ids) are compacted into a
-// queue with a warp prefix sum; every 32 hits make a round: the 32 point rows are gathered into
-// shared memory with 16-byte cp.async (6 lanes per row: whole sectors), double buffered so the
-// gather of round r+1 is in flight while round r is computed; then every lane takes ONE common
-// point and accumulates its 9x9 contribution into 81 registers.  No shared-memory or global
-// read-modify-write at all; the accumulators meet once per pair in a fixed-order butterfly.
+// ONE WARP PER CAMERA PAIR (i, k), k < i; every 32 common points make a round: their rows PT[j] are
+// gathered into shared memory with 16-byte cp.async (five lanes per row), double buffered so that the
+// gather of round r + 1 is in flight while round r is computed; every lane takes ONE common point.
+// No shared-memory or global read-modify-write; the per-lane sums meet once per pair in a fixed order.
 // Order of summation depends on the data only: runs are bit-reproducible.
 //
-// Bound: FP64 pipe (310 operations per pair-point; sum_j m_j (m_j - 1) / 2 pair-points).
+// Where the common points come from, and who adds up (history and measurements: DESIGN.md section 3b):
+//   * build_pair_index      once per engine: bitmaps per camera and -- memory permitting -- the STATIC
+//                           PAIR LISTS: the ascending ids of the points every pair shares
+//                           (pair_count_kernel, exclusive sum, pair_fill_kernel; 4 B per pair-point).
+//                           Visibility does not change between iterations; intersecting the bitmaps
+//                           and compacting the hits every solve was more than half of the kernel.
+//   * schur_pairs_reg_kernel<LIST = true>   the default: 32 ids per round with one coalesced load; the
+//                           pair's 9 x 9 block lives in 81 FP64 registers per lane (144 DFMAs per point).
+//   * schur_pairs_kernel<MINB, LIST>        the variant with the leading 8 x 8 of the block on DMMA.8x8x4
+//                           (operands transposed through shared memory); with LIST = false it scans
+//                           the bitmaps itself (4096 points per step, warp prefix sum, ring queue):
+//                           the path taken when the lists do not fit the memory budget.
+//   * schur_pairs_reg_kernel<LIST = false>  register accumulators with a lane-autonomous bitmap scan
+//                           (claimed 256-point groups); A/B runs only (BA_PAIRS_REG with BA_PAIRS_NO_LIST).
+//
+// Bound: FP64 pipe (~316 instructions per pair-point; sum_j m_j (m_j - 1) / 2 pair-points).  DMMA runs
+// on the same FP64 datapath as DFMA on this GPU (fp64_peak.cu, mode 2), so the tensor form buys no
+// arithmetic, only issue slots -- and costs the fragment traffic.
 //
 // schur_diag_kernel: the diagonal blocks P[9i..][9i..] and the rhs row, a segmented reduction over
 // the camera's observations in camera-major order (fixed chunking and order).
