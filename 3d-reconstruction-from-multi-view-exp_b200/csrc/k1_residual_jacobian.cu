@@ -11,6 +11,11 @@
 // Memory roofline (HBM): per observation 16 B read (x, y) [+8 B indices when sparse] and
 // 64 B + 160 B written (the point-side and camera-side Jacobian rows, each carrying the
 // residual so that the two consumers stream one row each).
+//
+// The row arithmetic itself is obs_jacobian / obs_residual / obs_cost in ba_common.cuh (one
+// division per observation, every operation pinned), shared with the kernels that re-derive the
+// rows: dense scenes are linearised matrix-free (k2_point_blocks.cu), K1 then only refreshes the
+// camera table and writes the rows when somebody reads the JP / JC buffers.
 #include "ba_common.cuh"
 
 namespace ba {

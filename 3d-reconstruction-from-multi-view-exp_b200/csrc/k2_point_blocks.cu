@@ -14,8 +14,14 @@
 // masked here, so the corresponding rows/columns of the reduced system vanish and K4 puts a
 // unit diagonal there (delta = 0, algebraically identical to deletion).
 //
-// Memory roofline (HBM): k2a reads 64 B/obs; cam reads 160 B/obs; k2b reads 64+160 B/obs and
-// writes 216 B/obs (Y).
+// Memory roofline (HBM), stored-row form (sparse scenes): k2a reads 64 B/obs; cam reads 160 B/obs;
+// k2b reads 64+160 B/obs and writes 216 B/obs (Y).
+//
+// Matrix-free form (template flag MF; dense scenes whose camera table fits 48 KB of shared memory,
+// dense_matrix_free): the three kernels re-derive the Jacobian rows with obs_jacobian (ba_common.cuh)
+// from the camera table, X_j and the observed point instead of reading what K1 stored -- the same
+// pinned arithmetic, the same summation orders, hence the same bits; K1 then stores nothing, k2a and
+// cam read 16 B/obs, k2b only writes its 216 B/obs.
 #include <cstdlib>
 
 #include "ba_common.cuh"

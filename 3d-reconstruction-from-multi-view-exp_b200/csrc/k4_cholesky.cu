@@ -7,7 +7,14 @@
 // right-hand side and is swept along as one more row, so after the factorisation it holds
 // y = L^-1 b.  Only L^T x = y is left for chol_backsolve_kernel.
 //
-// Per 64-column panel two launches:
+// Three regimes by size: n < 2048 -- the whole factorisation in ONE persistent cooperative launch
+// (chol_fused_kernel: the steps of chol_step_kernel with a grid barrier between them); n >= 2048 --
+// two-level blocking, per 64-column panel the two launches below and one rank-256 update on the
+// FP64 tensor cores per outer block (launch_chol_wide_update, divided over the ranks of a sharded
+// run).  Back substitution: one CTA (n < 1024), one 8-CTA cluster over distributed shared memory
+// (n < 2048), the whole grid (larger).
+//
+// Large systems, per 64-column panel two launches:
 //   chol_panel_kernel   every block eliminates the tall panel [diagonal block; its 64 rows] in
 //                       shared memory (re-factoring the diagonal block per block is cheaper than
 //                       a third launch, and the rows below need no separate triangular solve).
